@@ -1,0 +1,40 @@
+// Library context: one per GPU, owns the stream and the reusable device workspaces. Not thread-safe.
+#pragma once
+#include <string>
+#include <vector>
+#include "common.cuh"
+#include "factor.cuh"
+
+namespace gpslc {
+
+struct Ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    // factor workspaces: one slot per resident CTA
+    int slots = 0;
+    size_t slot_scratch_d = 0;   // doubles of L scratch per slot
+    size_t slot_z_d = 0;         // doubles of z/w scratch per slot
+    double* scratch = nullptr;
+    double* zbuf = nullptr;
+    unsigned int* counter = nullptr;  // work-queue counters (device)
+    unsigned long long launches = 0;  // kernels launched by this context (bench.py reports it)
+
+    int fail(int code, const std::string& msg) { last_error = msg; return code; }
+    int cuda_fail(cudaError_t e, const char* where) {
+        last_error = std::string(where) + ": " + cudaGetErrorString(e);
+        return GPSLC_ERR_CUDA;
+    }
+};
+
+#define GP_CUDA(ctx, call)                                                   \
+    do {                                                                     \
+        cudaError_t _e = (call);                                             \
+        if (_e != cudaSuccess) return (ctx)->cuda_fail(_e, #call);           \
+    } while (0)
+
+// make sure every slot can hold an NRB x NCB block matrix
+int ensure_workspace(Ctx* ctx, int NRB, int NCB);
+
+}  // namespace gpslc

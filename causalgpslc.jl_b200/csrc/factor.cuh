@@ -1,0 +1,492 @@
+// One-CTA blocked Cholesky + forward solves for one SPD matrix whose entries are produced on the fly by a
+// generator functor (RBF covariance build fused into the factorisation, or a dense matrix read, or the augmented
+// ITE matrix). Replaces, for one (chain, factor) pair, the reference's
+//   rbfKernelLog + processCov            (src/kernel.jl:24-59)
+//   Distributions.logpdf(MvNormal(0,K),y) (reached through Gen `mvnormal` at src/model_likelihood.jl:30-118)
+// i.e. LAPACK dpotrf + dtrsv + log-diag sum.
+//
+// Algorithm: left-looking, 64-wide panels. For panel j
+//   diag tile : C_jj = K_jj - sum_{J<j} L_jJ L_jJ^T          (DMMA m8n8k4, operands streamed by TMA bulk copies)
+//               w_j  = y_j  - sum_{J<j} L_jJ z_J             (fused in the same k-loop, plain DFMA)
+//   P2        : L_jj = chol(C_jj) (warp-shuffle 16x16 panels), Linv = L_jj^-1, z_j = Linv w_j, logdet += ...
+//   row tiles : C_Ij = K_Ij - sum_J L_IJ L_jJ^T  (128x64 per tile) ; L_Ij = C_Ij Linv^T (DMMA, A-fragments rebuilt
+//               from the accumulators with quad shuffles) ; L_Ij stored to the CTA's global scratch.
+// L lives in global scratch in an "atom" layout: every 8(row) x 4(k) DMMA operand fragment is 256 contiguous bytes,
+// fragments are grouped into 64(row) x 8(k) slabs of 4 KB so that one cp.async.bulk moves one pipeline operand.
+#pragma once
+#include "common.cuh"
+
+namespace gpslc {
+
+constexpr int NB = 64;                 // panel width == row-block height
+constexpr int KB = 8;                  // k extent of one pipeline slab
+constexpr int NSLAB = NB / KB;         // slabs per block
+constexpr int SLAB_D = NB * KB;        // doubles per slab (4 KB)
+constexpr int BLOCK_D = NB * NB;       // doubles per block (32 KB)
+constexpr int STAGES = 6;
+constexpr int PF = 4;                  // prefetch distance (slabs)
+constexpr int FWARPS = 8;
+constexpr int FTHREADS = FWARPS * 32;
+constexpr int STAGE_D = 3 * SLAB_D;    // A0 | A1 | B
+constexpr int MAXRHS = 2;
+constexpr int CS_LD = 65;              // P2 workspace leading dimension
+
+struct FactorOut {
+    double logdet;      // log det K
+    double gram[3];     // z0.z0, z0.z1, z1.z1 with z_i = L^-1 y_i
+    int info;           // 0, or 1-based index of the first non-positive pivot (LAPACK convention)
+};
+
+struct __align__(128) FactorSmem {
+    double stage[STAGES * STAGE_D];    // 72 KB; P2 aliases it as workspace while no copy is in flight
+    double linv[BLOCK_D];              // 32 KB; inverse of the current diagonal block, atom layout [n8][k4:16][32]
+    double wvec[MAXRHS][NB];           // w_j (pre-solve) / scratch
+    double red[32];
+    unsigned long long full[STAGES];
+    unsigned long long empty[STAGES];
+    FactorOut out;
+    int info;
+};
+
+// ---------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// FP64 tensor-core MMA (SASS: DMMA.8x8x4). A: lane holds A[lane/4][lane%4]; B: lane holds B[lane%4][lane/4];
+// C/D: lane holds rows lane/4, cols 2*(lane%4)+{0,1}.
+__device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+
+// ---------------------------------------------------------------------------------------------- scratch layout
+// blocks of panel J are contiguous: (I,J), I = J..NRB-1
+__device__ __host__ inline size_t block_off(int I, int J, int NRB) {
+    return ((size_t)J * NRB - (size_t)J * (J - 1) / 2 + (I - J)) * BLOCK_D;
+}
+__host__ __device__ inline size_t scratch_doubles(int NRB, int NCB) {
+    return ((size_t)NCB * NRB - (size_t)NCB * (NCB - 1) / 2) * BLOCK_D;
+}
+// element (r,c) inside a block: [slab c/8][r/8][k4 (c%8)/4][ (r%8)*4 + c%4 ]
+__device__ __host__ inline int elem_off(int r, int c) {
+    return (c >> 3) * SLAB_D + (r >> 3) * 64 + ((c >> 2) & 1) * 32 + (r & 7) * 4 + (c & 3);
+}
+__device__ __forceinline__ int linv_off(int n, int k) { return ((n >> 3) * 16 + (k >> 2)) * 32 + (n & 7) * 4 + (k & 3); }
+
+__device__ inline void factor_smem_init(FactorSmem& sm) {
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], FWARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------- P2
+// Factor the 64x64 block held in Cs (row-major, CS_LD, lower triangle valid), leave L in Cs, L^-1 in sm.linv.
+// ws = workspace after Cs. Returns via sm.info (first bad pivot, 1-based global column) if any.
+__device__ inline void p2_factor_diag(FactorSmem& sm, double* Cs, double* ws, int col0) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* li16 = ws;            // [4][16][17]  inverse of the 16x16 diagonal sub-blocks, li16[b][i][c] = X[i][c]
+    double* Ts = ws + 4 * 16 * 17; // [3][16][17]
+    const unsigned FULL = 0xffffffffu;
+    for (int jb = 0; jb < 4; jb++) {
+        const int c0 = jb * 16;
+        if (warp == 0) {
+            const int r = lane & 15;
+            double a[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) a[k] = (k <= r) ? Cs[(c0 + r) * CS_LD + c0 + k] : 0.0;
+            double rinv_r = 0.0;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                double akk = __shfl_sync(FULL, a[k], k);
+                if (!(akk > 0.0)) {
+                    if (lane == 0 && sm.info == 0) sm.info = col0 + c0 + k + 1;
+                    akk = 1.0;
+                }
+                double ri = rsqrt(akk);
+                double lk = a[k] * ri;
+                a[k] = lk;
+                if (r == k) rinv_r = ri;
+#pragma unroll
+                for (int j = k + 1; j < 16; j++) {
+                    double ljk = __shfl_sync(FULL, lk, j);
+                    a[j] = fma(-lk, ljk, a[j]);
+                }
+            }
+            // inverse, lane c (= r) owns column c of X = L16^-1
+            double x[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                double rii = __shfl_sync(FULL, rinv_r, i);
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < i; k++) {
+                    double lik = __shfl_sync(FULL, a[k], i);
+                    s = fma(lik, x[k], s);
+                }
+                x[i] = (i == r) ? rii : ((i > r) ? -s * rii : 0.0);
+            }
+            if (lane < 16) {
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    if (k <= r) Cs[(c0 + r) * CS_LD + c0 + k] = a[k];
+                    li16[(jb * 16 + k) * 17 + r] = x[k];
+                }
+            }
+        }
+        __syncthreads();
+        const int R = NB - c0 - 16;   // rows below the sub-block
+        if (R > 0) {
+            // TRSM: X[row][col] = sum_{k<=col} A[row][k] * Linv16[col][k]
+            if (tid < R * 4) {
+                const int row = c0 + 16 + (tid >> 2), cq = tid & 3;
+                double arow[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) arow[k] = Cs[row * CS_LD + c0 + k];
+                __syncwarp();
+                double o[4];
+#pragma unroll
+                for (int cc = 0; cc < 4; cc++) {
+                    const int col = cq * 4 + cc;
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 16; k++)
+                        if (k <= col) s = fma(arow[k], li16[(jb * 16 + col) * 17 + k], s);
+                    o[cc] = s;
+                }
+#pragma unroll
+                for (int cc = 0; cc < 4; cc++) Cs[row * CS_LD + c0 + cq * 4 + cc] = o[cc];
+            }
+            __syncthreads();
+            // SYRK on the trailing part
+            const int base = c0 + 16;
+            for (int idx = tid; idx < R * R; idx += FTHREADS) {
+                const int rr = idx / R, cc = idx - rr * R;
+                if (cc <= rr) {
+                    const double* pr = Cs + (base + rr) * CS_LD + c0;
+                    const double* pc = Cs + (base + cc) * CS_LD + c0;
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 16; k++) s = fma(pr[k], pc[k], s);
+                    Cs[(base + rr) * CS_LD + base + cc] -= s;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- full inverse into sm.linv (atom layout). Diagonal 16-blocks first (with explicit zeros above the diagonal).
+    for (int idx = tid; idx < 4 * 256; idx += FTHREADS) {
+        const int b = idx >> 8, i = (idx >> 4) & 15, c = idx & 15;
+        sm.linv[linv_off(b * 16 + i, b * 16 + c)] = li16[(b * 16 + i) * 17 + c];
+    }
+    __syncthreads();
+    for (int d = 1; d < 4; d++) {
+        const int nblk = 4 - d;
+        // T_ij = sum_{k=j}^{i-1} L_ik X_kj
+        for (int idx = tid; idx < nblk * 256; idx += FTHREADS) {
+            const int bi = idx >> 8, a = (idx >> 4) & 15, b = idx & 15;
+            const int i = d + bi, j = bi;
+            double s = 0.0;
+            for (int k = j; k < i; k++) {
+#pragma unroll
+                for (int m = 0; m < 16; m++)
+                    s = fma(Cs[(16 * i + a) * CS_LD + 16 * k + m], sm.linv[linv_off(16 * k + m, 16 * j + b)], s);
+            }
+            Ts[(bi * 16 + a) * 17 + b] = s;
+        }
+        __syncthreads();
+        // X_ij = -X_ii T_ij
+        for (int idx = tid; idx < nblk * 256; idx += FTHREADS) {
+            const int bi = idx >> 8, a = (idx >> 4) & 15, b = idx & 15;
+            const int i = d + bi, j = bi;
+            double s = 0.0;
+#pragma unroll
+            for (int m = 0; m < 16; m++)
+                if (m <= a) s = fma(li16[(i * 16 + a) * 17 + m], Ts[(bi * 16 + m) * 17 + b], s);
+            sm.linv[linv_off(16 * i + a, 16 * j + b)] = -s;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- main routine
+struct Pipe { uint32_t produced; uint32_t consumed; };
+
+// Gen concept:
+//   void quad(int r0, int r1, int c, double& v00, double& v01, double& v10, double& v11) const
+//        -> K[r0][c], K[r0][c+1], K[r1][c], K[r1][c+1]   (lower triangle / rectangular rows; c even)
+//   double rhs(int which, int r) const
+template <class Gen>
+__device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const int nrhs, double* scratch,
+                           double* zbuf /* [MAXRHS][NCB*NB] solves, then [MAXRHS][NCB*NB] pre-solve w */,
+                           FactorSmem& sm, Pipe& pipe) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int npad = NCB * NB;
+    double logdet_part = 0.0, g00 = 0.0, g01 = 0.0, g11 = 0.0;
+    if (tid == 0) sm.info = 0;
+    __syncthreads();
+
+    for (int j = 0; j < NCB; j++) {
+        const int T = j * NSLAB;  // slabs in the k-loop of this panel
+        // =================================================================== diagonal tile
+        {
+            double acc[8][2];
+#pragma unroll
+            for (int ni = 0; ni < 8; ni++) { acc[ni][0] = 0.0; acc[ni][1] = 0.0; }
+            double wsum[MAXRHS] = {0.0, 0.0};
+            const int wr = tid >> 2, kq = tid & 3;  // RHS update mapping: row wr, k pair kq
+            auto produce = [&](int t) {
+                const uint32_t gi = pipe.produced++;
+                const int st = gi % STAGES;
+                if (gi >= STAGES) mbar_wait(&sm.empty[st], ((gi / STAGES) - 1) & 1);
+                mbar_expect_tx(&sm.full[st], SLAB_D * 8);
+                const int J = t >> 3, s = t & 7;
+                bulk_g2s(sm.stage + st * STAGE_D + 2 * SLAB_D, scratch + block_off(j, J, NRB) + s * SLAB_D, SLAB_D * 8,
+                         &sm.full[st]);
+            };
+            if (tid == 0) for (int t = 0; t < PF && t < T; t++) produce(t);
+            for (int t = 0; t < T; t++) {
+                if (tid == 0 && t + PF < T) produce(t + PF);
+                const uint32_t gi = pipe.consumed++;
+                const int st = gi % STAGES;
+                mbar_wait(&sm.full[st], (gi / STAGES) & 1);
+                const double* sB = sm.stage + st * STAGE_D + 2 * SLAB_D;
+#pragma unroll
+                for (int k4 = 0; k4 < 2; k4++) {
+                    const double a = sB[(warp * 2 + k4) * 32 + lane];
+#pragma unroll
+                    for (int ni = 0; ni < 8; ni++) {
+                        if (ni <= warp) {
+                            const double b = sB[(ni * 2 + k4) * 32 + lane];
+                            dmma(acc[ni], a, b);
+                        }
+                    }
+                }
+                if (nrhs > 0) {
+                    // rows wr, columns (kq*2, kq*2+1) of the slab
+                    const double2 l2 = *reinterpret_cast<const double2*>(sB + (wr >> 3) * 64 + (kq >> 1) * 32 + (wr & 7) * 4 + (kq & 1) * 2);
+                    const int kcol = t * KB + kq * 2;
+                    for (int rh = 0; rh < nrhs; rh++) {
+                        const double2 z2 = *reinterpret_cast<const double2*>(zbuf + (size_t)rh * npad + kcol);
+                        wsum[rh] = fma(l2.x, z2.x, fma(l2.y, z2.y, wsum[rh]));
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.empty[st]);
+            }
+            __syncthreads();  // every warp is done with the stage buffers -> P2 may alias them
+            double* Cs = sm.stage;
+            double* ws = sm.stage + NB * CS_LD;
+            // C_jj = K_jj - acc  (lower tiles only)
+            {
+                const int r = j * NB + warp * 8 + g;
+#pragma unroll
+                for (int ni = 0; ni < 8; ni++) {
+                    if (ni <= warp) {
+                        const int c = j * NB + ni * 8 + 2 * q;
+                        double v00, v01, v10, v11;
+                        gen.quad(r, r, c, v00, v01, v10, v11);
+                        Cs[(warp * 8 + g) * CS_LD + ni * 8 + 2 * q] = v00 - acc[ni][0];
+                        Cs[(warp * 8 + g) * CS_LD + ni * 8 + 2 * q + 1] = v01 - acc[ni][1];
+                    }
+                }
+            }
+            for (int rh = 0; rh < nrhs; rh++) {
+                double s = wsum[rh];
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                if (kq == 0) sm.wvec[rh][wr] = gen.rhs(rh, j * NB + wr) - s;
+            }
+            __syncthreads();
+            p2_factor_diag(sm, Cs, ws, j * NB);
+            // store L_jj (lower, zeros above), log-diagonal, z_j = Linv w_j
+            {
+                double* dst = scratch + block_off(j, j, NRB);
+                for (int idx = tid; idx < BLOCK_D; idx += FTHREADS) {
+                    const int r = idx >> 6, c = idx & 63;
+                    dst[elem_off(r, c)] = (c <= r) ? Cs[r * CS_LD + c] : 0.0;
+                }
+                if (tid < NB) logdet_part += log(Cs[tid * CS_LD + tid]);
+                if (tid < NB * nrhs) {
+                    const int rh = tid >> 6, r = tid & 63;
+                    double s = 0.0;
+                    for (int c = 0; c <= r; c++) s = fma(sm.linv[linv_off(r, c)], sm.wvec[rh][c], s);
+                    zbuf[(size_t)rh * npad + j * NB + r] = s;
+                    zbuf[(size_t)(MAXRHS + rh) * npad + j * NB + r] = sm.wvec[rh][r];
+                }
+            }
+            __syncthreads();
+            if (tid < NB && nrhs > 0) {
+                // gram sums: read back z from global (just written by this CTA; visible after the barrier)
+                const double z0 = zbuf[j * NB + tid];
+                g00 = fma(z0, z0, g00);
+                if (nrhs > 1) {
+                    const double z1 = zbuf[(size_t)npad + j * NB + tid];
+                    g01 = fma(z0, z1, g01);
+                    g11 = fma(z1, z1, g11);
+                }
+            }
+            fence_proxy_async();   // generic-proxy writes (smem workspace, global L_jj) before later async-proxy copies
+            __syncthreads();
+        }
+        // =================================================================== row tiles below the diagonal
+        const int nblk = NRB - j - 1;
+        const int ntile = (nblk + 1) >> 1;
+        const int F = ntile * T;
+        auto produce = [&](int f) {
+            const int tile = f / T, t = f - tile * T;
+            const int I0 = j + 1 + 2 * tile;
+            const bool two = (I0 + 1 < NRB);
+            const uint32_t gi = pipe.produced++;
+            const int st = gi % STAGES;
+            if (gi >= STAGES) mbar_wait(&sm.empty[st], ((gi / STAGES) - 1) & 1);
+            mbar_expect_tx(&sm.full[st], (two ? 3 : 2) * SLAB_D * 8);
+            const int J = t >> 3, s = t & 7;
+            double* dst = sm.stage + st * STAGE_D;
+            bulk_g2s(dst, scratch + block_off(I0, J, NRB) + s * SLAB_D, SLAB_D * 8, &sm.full[st]);
+            if (two) bulk_g2s(dst + SLAB_D, scratch + block_off(I0 + 1, J, NRB) + s * SLAB_D, SLAB_D * 8, &sm.full[st]);
+            bulk_g2s(dst + 2 * SLAB_D, scratch + block_off(j, J, NRB) + s * SLAB_D, SLAB_D * 8, &sm.full[st]);
+        };
+        if (tid == 0) for (int f = 0; f < PF && f < F; f++) produce(f);
+        int f = 0;
+        const int half = warp >> 2, rw = warp & 3;
+        for (int tile = 0; tile < ntile; tile++) {
+            const int I0 = j + 1 + 2 * tile;
+            const bool active = (I0 + half < NRB);
+            double acc[2][8][2];
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 8; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+            for (int t = 0; t < T; t++, f++) {
+                if (tid == 0 && f + PF < F) produce(f + PF);
+                const uint32_t gi = pipe.consumed++;
+                const int st = gi % STAGES;
+                mbar_wait(&sm.full[st], (gi / STAGES) & 1);
+                if (active) {
+                    const double* sA = sm.stage + st * STAGE_D + half * SLAB_D + (rw * 2) * 64;
+                    const double* sB = sm.stage + st * STAGE_D + 2 * SLAB_D;
+#pragma unroll
+                    for (int k4 = 0; k4 < 2; k4++) {
+                        const double a0 = sA[k4 * 32 + lane];
+                        const double a1 = sA[64 + k4 * 32 + lane];
+#pragma unroll
+                        for (int ni = 0; ni < 8; ni++) {
+                            const double b = sB[(ni * 2 + k4) * 32 + lane];
+                            dmma(acc[0][ni], a0, b);
+                            dmma(acc[1][ni], a1, b);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.empty[st]);
+            }
+            if (active) {
+                const int I = I0 + half;
+                // C = K - acc
+                const int r0 = I * NB + rw * 16 + g;
+#pragma unroll
+                for (int ni = 0; ni < 8; ni++) {
+                    const int c = j * NB + ni * 8 + 2 * q;
+                    double v00, v01, v10, v11;
+                    gen.quad(r0, r0 + 8, c, v00, v01, v10, v11);
+                    acc[0][ni][0] = v00 - acc[0][ni][0];
+                    acc[0][ni][1] = v01 - acc[0][ni][1];
+                    acc[1][ni][0] = v10 - acc[1][ni][0];
+                    acc[1][ni][1] = v11 - acc[1][ni][1];
+                }
+                // L_Ij = C Linv^T : out[:, ni] = sum_{kc <= 2ni+1} Afrag(kc) x Linv[ni-tile rows][kc]
+                double* dst = scratch + block_off(I, j, NRB);
+#pragma unroll
+                for (int nig = 0; nig < 8; nig += 4) {
+                    double o[2][4][2];
+#pragma unroll
+                    for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                        for (int nn = 0; nn < 4; nn++) { o[mi][nn][0] = 0.0; o[mi][nn][1] = 0.0; }
+#pragma unroll
+                    for (int kc = 0; kc < 16; kc++) {
+                        if (kc <= 2 * (nig + 3) + 1) {
+                            const int tt = kc >> 1, hh = kc & 1;
+                            const int src = (lane & ~3) | (2 * hh + (q >> 1));
+                            double a[2];
+#pragma unroll
+                            for (int mi = 0; mi < 2; mi++) {
+                                const double v0 = __shfl_sync(0xffffffffu, acc[mi][tt][0], src);
+                                const double v1 = __shfl_sync(0xffffffffu, acc[mi][tt][1], src);
+                                a[mi] = (q & 1) ? v1 : v0;
+                            }
+#pragma unroll
+                            for (int nn = 0; nn < 4; nn++) {
+                                const int ni = nig + nn;
+                                if (kc <= 2 * ni + 1) {
+                                    const double b = sm.linv[(ni * 16 + kc) * 32 + lane];
+                                    dmma(o[0][nn], a[0], b);
+                                    dmma(o[1][nn], a[1], b);
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                        for (int nn = 0; nn < 4; nn++) {
+                            const int ni = nig + nn;
+                            double2 v = make_double2(o[mi][nn][0], o[mi][nn][1]);
+                            *reinterpret_cast<double2*>(dst + ni * SLAB_D + (rw * 2 + mi) * 64 + (q >> 1) * 32 + g * 4 + (q & 1) * 2) = v;
+                        }
+                }
+            }
+        }
+        fence_proxy_async();
+        __syncthreads();
+    }
+    // ---- block reductions
+    double vals[4] = {logdet_part, g00, g01, g11};
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+        double s = vals[v];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) sm.red[warp * 4 + v] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double s[4] = {0, 0, 0, 0};
+        for (int w = 0; w < FWARPS; w++)
+            for (int v = 0; v < 4; v++) s[v] += sm.red[w * 4 + v];
+        sm.out.logdet = 2.0 * s[0];
+        sm.out.gram[0] = s[1]; sm.out.gram[1] = s[2]; sm.out.gram[2] = s[3];
+        sm.out.info = sm.info;
+    }
+    __syncthreads();
+}
+
+}  // namespace gpslc

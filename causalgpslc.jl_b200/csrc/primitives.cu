@@ -1,0 +1,198 @@
+// Deterministic primitives of the C ABI (parity layer): covariance build, batched Cholesky log-density on dense
+// input, and the fused build+Cholesky log-density. See include/gpslc.h for the reference call sites each replaces.
+#include "context.cuh"
+#include "gens.cuh"
+
+namespace gpslc {
+
+int ensure_workspace(Ctx* ctx, int NRB, int NCB) {
+    const size_t need = scratch_doubles(NRB, NCB);
+    const size_t needz = (size_t)2 * MAXRHS * NCB * NB;
+    if (ctx->slots == 0) ctx->slots = 2 * ctx->num_sms;
+    if (need > ctx->slot_scratch_d) {
+        if (ctx->scratch) cudaFree(ctx->scratch);
+        ctx->scratch = nullptr;
+        GP_CUDA(ctx, cudaMalloc(&ctx->scratch, need * ctx->slots * sizeof(double)));
+        ctx->slot_scratch_d = need;
+    }
+    if (needz > ctx->slot_z_d) {
+        if (ctx->zbuf) cudaFree(ctx->zbuf);
+        ctx->zbuf = nullptr;
+        GP_CUDA(ctx, cudaMalloc(&ctx->zbuf, needz * ctx->slots * sizeof(double)));
+        ctx->slot_z_d = needz;
+    }
+    if (!ctx->counter) GP_CUDA(ctx, cudaMalloc(&ctx->counter, 64 * sizeof(unsigned int)));
+    return GPSLC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ cov build
+// Materialised covariance (HBM-bound): K[b] (n x n, column-major) for `batch` parameter sets. One thread computes a
+// 1x4 strip of a column block so that stores are 32-byte vectors along the fastest (row) dimension.
+// feat: [batch or 1][D][n] feature columns (row-contiguous), w: [batch][D], scale/noise: [batch].
+// X2 != X1 is supported (likelihood.jl:27 builds K(T, doT)).
+__global__ void __launch_bounds__(256) cov_build_kernel(int n, int D, const double* __restrict__ f1, const double* __restrict__ f2,
+                                                        size_t feat_stride, const double* __restrict__ w,
+                                                        const double* __restrict__ scale, const double* __restrict__ noise,
+                                                        int has_noise, double* __restrict__ K) {
+    extern __shared__ double sh[];  // [D] weights, then [D][64] column features, then [D][64*? ] row features
+    const int b = blockIdx.z;
+    const int r0 = blockIdx.x * 128, c0 = blockIdx.y * 32;
+    double* sw = sh;
+    double* sc = sh + D;            // [D][32]  features of the tile's columns (from f2)
+    double* sr = sc + D * 32;       // [D][128] features of the tile's rows (from f1)
+    const double* p1 = f1 + (size_t)b * feat_stride;
+    const double* p2 = f2 + (size_t)b * feat_stride;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) sw[i] = w[(size_t)b * D + i];
+    for (int i = threadIdx.x; i < D * 32; i += blockDim.x) {
+        const int d = i >> 5, c = c0 + (i & 31);
+        sc[i] = (c < n) ? p2[(size_t)d * n + c] : 0.0;
+    }
+    for (int i = threadIdx.x; i < D * 128; i += blockDim.x) {
+        const int d = i >> 7, r = r0 + (i & 127);
+        sr[i] = (r < n) ? p1[(size_t)d * n + r] : 0.0;
+    }
+    __syncthreads();
+    const double s = scale[b];
+    const double nz = has_noise ? noise[b] : 0.0;
+    // thread t: rows (t%32)*4 .. +3, columns (t/32)*4 .. +3
+    const int tr = (threadIdx.x & 31) * 4, tc = (threadIdx.x >> 5) * 4;
+    double acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) acc[j][i] = 0.0;
+    for (int d = 0; d < D; d++) {
+        const double wd = sw[d];
+        double zr[4], zc[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) zr[i] = sr[d * 128 + tr + i];
+#pragma unroll
+        for (int j = 0; j < 4; j++) zc[j] = sc[d * 32 + tc + j];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const double t = zr[i] - zc[j];
+                acc[j][i] = fma(t * wd, t, acc[j][i]);
+            }
+    }
+    double* Kb = K + (size_t)b * n * n;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int c = c0 + tc + j;
+        if (c >= n) continue;
+        double v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            v[i] = s * exp(-acc[j][i]);
+            if (has_noise && (r0 + tr + i) == c) v[i] += nz;
+        }
+        const int r = r0 + tr;
+        double* dst = Kb + (size_t)c * n + r;
+        if (r + 3 < n && ((((size_t)c * n + r) & 3) == 0) && ((reinterpret_cast<uintptr_t>(Kb) & 31) == 0)) {
+            // 32-byte vector store
+            double4 v4 = make_double4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<double4*>(dst) = v4;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (r + i < n) dst[i] = v[i];
+        }
+    }
+}
+
+int launch_cov_build(Ctx* ctx, int n, int batch, int D, const double* f1, const double* f2, size_t feat_stride,
+                     const double* w, const double* scale, const double* noise, double* K) {
+    dim3 grid(ceil_div(n, 128), ceil_div(n, 32), batch);
+    size_t sh = (size_t)(D + D * 32 + D * 128) * sizeof(double);
+    cov_build_kernel<<<grid, 256, sh, ctx->stream>>>(n, D, f1, f2, feat_stride, w, scale, noise, noise != nullptr, K);
+    ctx->launches++;
+    GP_CUDA(ctx, cudaGetLastError());
+    return GPSLC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ batched logpdf
+struct LogpdfJobDense { const double* K; const double* y; int n; int ld; };
+
+template <bool FUSED>
+__global__ void __launch_bounds__(FTHREADS, 2)
+batched_logpdf_kernel(int batch, int n, const double* __restrict__ Kall, int ld, const double* __restrict__ yall, int y_shared,
+                      // fused build inputs
+                      int D, const double* __restrict__ feat, size_t feat_stride, const double* __restrict__ w,
+                      const double* __restrict__ scale, const double* __restrict__ noise,
+                      double* scratch, size_t slot_scratch, double* zbuf, size_t slot_z, unsigned int* counter,
+                      double* logpdf, double* logdet_out, double* quad_out, int* info) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FactorSmem& sm = *reinterpret_cast<FactorSmem*>(smem_raw);
+    __shared__ RbfSpec spec;
+    __shared__ unsigned int job;
+    factor_smem_init(sm);
+    Pipe pipe{0, 0};
+    const int NCB = ceil_div(n, NB);
+    double* my_scratch = scratch + (size_t)blockIdx.x * slot_scratch;
+    double* my_z = zbuf + (size_t)blockIdx.x * slot_z;
+    for (;;) {
+        if (threadIdx.x == 0) job = atomicAdd(counter, 1u);
+        __syncthreads();
+        const unsigned int b = job;
+        if (b >= (unsigned)batch) break;
+        const double* y = yall + (y_shared ? 0 : (size_t)b * n);
+        if (FUSED) {
+            if (threadIdx.x == 0) {
+                spec.D = D; spec.n = n; spec.scale = scale[b]; spec.noise = noise[b];
+                spec.y[0] = y; spec.y[1] = y;
+            }
+            for (int d = threadIdx.x; d < D; d += blockDim.x) {
+                spec.feat[d] = feat + (size_t)b * feat_stride + (size_t)d * n;
+                spec.w[d] = w[(size_t)b * D + d];
+            }
+            __syncthreads();
+            RbfGen gen{&spec};
+            factor_run(gen, NCB, NCB, 1, my_scratch, my_z, sm, pipe);
+        } else {
+            DenseGen gen{Kall + (size_t)b * ld * n, {y, y}, n, ld};
+            factor_run(gen, NCB, NCB, 1, my_scratch, my_z, sm, pipe);
+        }
+        if (threadIdx.x == 0) {
+            const FactorOut o = sm.out;
+            if (logdet_out) logdet_out[b] = o.logdet;
+            if (quad_out) quad_out[b] = o.gram[0];
+            if (info) info[b] = o.info;
+            if (logpdf) logpdf[b] = (o.info == 0) ? -0.5 * (n * LOG_2PI + o.logdet + o.gram[0]) : -INFINITY;
+        }
+        __syncthreads();
+    }
+}
+
+template <bool FUSED>
+static int launch_batched(Ctx* ctx, int batch, int n, const double* K, int ld, const double* y, int y_shared, int D,
+                          const double* feat, size_t feat_stride, const double* w, const double* scale,
+                          const double* noise, double* logpdf, double* logdet, double* quad, int* info) {
+    const int NCB = ceil_div(n, NB);
+    int rc = ensure_workspace(ctx, NCB, NCB);
+    if (rc) return rc;
+    auto kern = batched_logpdf_kernel<FUSED>;
+    GP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
+    GP_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, sizeof(unsigned int), ctx->stream));
+    const int grid = batch < ctx->slots ? batch : ctx->slots;
+    kern<<<grid, FTHREADS, sizeof(FactorSmem), ctx->stream>>>(batch, n, K, ld, y, y_shared, D, feat, feat_stride, w, scale,
+                                                             noise, ctx->scratch, ctx->slot_scratch_d, ctx->zbuf,
+                                                             ctx->slot_z_d, ctx->counter, logpdf, logdet, quad, info);
+    ctx->launches++;
+    GP_CUDA(ctx, cudaGetLastError());
+    return GPSLC_OK;
+}
+
+int launch_chol_logpdf_dense(Ctx* ctx, int batch, int n, const double* K, int ld, const double* y, int y_shared,
+                             double* logpdf, double* logdet, double* quad, int* info) {
+    return launch_batched<false>(ctx, batch, n, K, ld, y, y_shared, 0, nullptr, 0, nullptr, nullptr, nullptr, logpdf, logdet,
+                                 quad, info);
+}
+int launch_rbf_logpdf(Ctx* ctx, int batch, int n, int D, const double* feat, size_t feat_stride, const double* w,
+                      const double* scale, const double* noise, const double* y, int y_shared, double* logpdf,
+                      double* logdet, double* quad, int* info) {
+    return launch_batched<true>(ctx, batch, n, nullptr, 0, y, y_shared, D, feat, feat_stride, w, scale, noise, logpdf, logdet,
+                                quad, info);
+}
+
+}  // namespace gpslc
