@@ -179,3 +179,131 @@ int gpslc_rbf_logpdf(gpslc_ctx* h, int loc, int n, int batch, int D, const doubl
 }
 
 }  // extern "C"
+
+// ================================================================================================ sampler
+#include "sampler.cuh"
+namespace gpslc {
+int sampler_create(Ctx*, int, int, int, int, int, const double*, const double*, const double*, int, const int*, double, double,
+                   const double*, const double*, double, int, int, int, unsigned long long, int, int, int, int, Sampler**);
+void sampler_free(Sampler*);
+int sampler_init(Sampler*);
+int sampler_run(Sampler*, int);
+int sampler_mh_sweeps(Sampler*, int);
+int sampler_ess_pass(Sampler*, int);
+int sampler_get_state(Sampler*, double*);
+int sampler_set_state(Sampler*, int, const double*);
+}
+struct gpslc_sampler { Sampler* s; };
+
+extern "C" {
+
+int gpslc_sampler_create(gpslc_ctx* h, int loc, const gpslc_data* d, const gpslc_prior* p, const gpslc_opts* o, gpslc_sampler** out) {
+    if (!h || !out) return GPSLC_ERR_ARG;
+    Ctx* ctx = &h->c;
+    *out = nullptr;
+    if (!d || !p || !o) return ctx->fail(GPSLC_ERR_ARG, "gpslc_sampler_create: null argument");
+    if (o->nOuter < 0 || o->nMHInner < 0 || o->nESInner < 0) return ctx->fail(GPSLC_ERR_ARG, "gpslc_sampler_create: negative iteration count");
+    Sampler* s = nullptr;
+    GP_TRY(sampler_create(ctx, loc, d->n, d->nX, d->nU, d->binary, d->X, d->T, d->Y, d->n_obj, d->obj_counts, d->sigma_u_eps,
+                          d->sigma_u_cov, p->shape, p->scale, p->drift, o->nMHInner, o->nESInner, o->n_chains, o->seed,
+                          o->chain_offset, o->u_layout_mode, o->ess_rule, o->observe_x, &s));
+    int rc = sampler_init(s);
+    if (rc) { sampler_free(s); return rc; }
+    *out = new gpslc_sampler{s};
+    return GPSLC_OK;
+}
+
+void gpslc_sampler_destroy(gpslc_sampler* hs) {
+    if (!hs) return;
+    sampler_free(hs->s);
+    delete hs;
+}
+
+int gpslc_sampler_layout(const gpslc_sampler* hs, int* n_params, int* stride, int* n_sites, int* n_factors) {
+    if (!hs) return GPSLC_ERR_ARG;
+    if (n_params) *n_params = hs->s->m.n_params;
+    if (stride) *stride = hs->s->m.stride;
+    if (n_sites) *n_sites = hs->s->m.n_sites;
+    if (n_factors) *n_factors = hs->s->m.nF;
+    return GPSLC_OK;
+}
+
+int gpslc_sampler_run(gpslc_sampler* hs, int n_outer) {
+    if (!hs || n_outer < 0) return GPSLC_ERR_ARG;
+    GP_CUDA(hs->s->ctx, cudaSetDevice(hs->s->ctx->device));
+    return sampler_run(hs->s, n_outer);
+}
+int gpslc_sampler_mh_sweeps(gpslc_sampler* hs, int count) {
+    if (!hs || count < 0) return GPSLC_ERR_ARG;
+    GP_CUDA(hs->s->ctx, cudaSetDevice(hs->s->ctx->device));
+    return sampler_mh_sweeps(hs->s, count);
+}
+int gpslc_sampler_ess_pass(gpslc_sampler* hs, int pass_index) {
+    if (!hs) return GPSLC_ERR_ARG;
+    GP_CUDA(hs->s->ctx, cudaSetDevice(hs->s->ctx->device));
+    return sampler_ess_pass(hs->s, pass_index);
+}
+
+int gpslc_sampler_get_samples(gpslc_sampler* hs, int loc, double* out, int* outer_done) {
+    if (!hs) return GPSLC_ERR_ARG;
+    Sampler* s = hs->s; Ctx* ctx = s->ctx;
+    if (outer_done) *outer_done = s->outer_done;
+    if (out && s->outer_done > 0) {
+        const size_t bytes = (size_t)s->outer_done * s->m.n_chains * s->m.stride * sizeof(double);
+        GP_CUDA(ctx, cudaMemcpyAsync(out, s->samples, bytes, loc == 1 ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GPSLC_OK;
+}
+const double* gpslc_sampler_samples_device(gpslc_sampler* hs) { return hs ? hs->s->samples : nullptr; }
+
+int gpslc_sampler_get_state(gpslc_sampler* hs, int loc, double* packed) {
+    if (!hs || !packed) return GPSLC_ERR_ARG;
+    Sampler* s = hs->s; Ctx* ctx = s->ctx;
+    const size_t count = (size_t)s->m.n_chains * s->m.stride;
+    if (loc == 1) { GP_TRY(sampler_get_state(s, packed)); GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); return GPSLC_OK; }
+    double* tmp = nullptr;
+    GP_CUDA(ctx, cudaMalloc(&tmp, count * sizeof(double)));
+    int rc = sampler_get_state(s, tmp);
+    cudaError_t e = cudaMemcpyAsync(packed, tmp, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(tmp);
+    if (rc) return rc;
+    if (e != cudaSuccess) return ctx->cuda_fail(e, "gpslc_sampler_get_state");
+    if (e2 != cudaSuccess) return ctx->cuda_fail(e2, "gpslc_sampler_get_state");
+    return GPSLC_OK;
+}
+int gpslc_sampler_set_state(gpslc_sampler* hs, int loc, const double* packed) {
+    if (!hs || !packed) return GPSLC_ERR_ARG;
+    return sampler_set_state(hs->s, loc, packed);
+}
+int gpslc_sampler_get_terms(gpslc_sampler* hs, double* factor_logpdf, double* u_quad) {
+    if (!hs) return GPSLC_ERR_ARG;
+    Sampler* s = hs->s; Ctx* ctx = s->ctx;
+    if (factor_logpdf) GP_CUDA(ctx, cudaMemcpyAsync(factor_logpdf, s->c.lp, (size_t)s->m.n_chains * s->m.nF * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (u_quad && s->m.nU > 0) GP_CUDA(ctx, cudaMemcpyAsync(u_quad, s->c.q, (size_t)s->m.n_chains * s->m.nU * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GPSLC_OK;
+}
+int gpslc_sampler_get_stats(gpslc_sampler* hs, unsigned long long* accepts, unsigned long long* ess_evals) {
+    if (!hs) return GPSLC_ERR_ARG;
+    Sampler* s = hs->s; Ctx* ctx = s->ctx;
+    if (accepts) GP_CUDA(ctx, cudaMemcpyAsync(accepts, s->c.accepts, (size_t)s->m.n_chains * s->m.n_sites * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ess_evals) GP_CUDA(ctx, cudaMemcpyAsync(ess_evals, s->c.ess_evals, (size_t)s->m.n_chains * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GPSLC_OK;
+}
+
+int gpslc_posterior(gpslc_ctx* h, const gpslc_data* d, const gpslc_prior* p, const gpslc_opts* o, double* samples_out,
+                    unsigned long long* accepts, unsigned long long* ess_evals) {
+    if (!h || !o) return GPSLC_ERR_ARG;
+    gpslc_sampler* hs = nullptr;
+    GP_TRY(gpslc_sampler_create(h, GPSLC_HOST, d, p, o, &hs));
+    int rc = gpslc_sampler_run(hs, o->nOuter);
+    if (!rc) rc = gpslc_sampler_get_samples(hs, GPSLC_HOST, samples_out, nullptr);
+    if (!rc) rc = gpslc_sampler_get_stats(hs, accepts, ess_evals);
+    gpslc_sampler_destroy(hs);
+    return rc;
+}
+
+}  // extern "C"

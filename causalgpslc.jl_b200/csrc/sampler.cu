@@ -1,0 +1,756 @@
+// Many-chain posterior sampler: Gen `generate` + nOuter x (nMHInner single-site MH sweeps + nESInner elliptical-slice
+// passes), i.e. all eight `Posterior` methods of src/inference.jl:4-379, for thousands of independent chains.
+//
+// What differs from the reference by design (values identical, cost not — SURVEY.md App. A4/B2):
+//  * a single-site update re-scores only the GP factor the site feeds (the reference re-executes the whole model);
+//  * within a sweep the sites of different factors are conditionally independent given U, so each (chain, factor)
+//    "lane" runs its own sites sequentially on one CTA while other lanes run elsewhere; with the counter-based RNG
+//    keyed by (chain, sweep, site) the result is the one the sequential sweep would produce;
+//  * the U prior N(0, uNoise*SigmaU) uses the closed form of the block matrix — no factorisation.
+#include <algorithm>
+#include <string>
+#include "sampler.cuh"
+#include "capi_util.cuh"
+
+namespace gpslc {
+
+// ------------------------------------------------------------------------------------------------ device helpers
+
+__device__ __forceinline__ double ig_logpdf(double x, double shape, double scale) {
+    if (!(x > 0.0)) return -INFINITY;
+    return shape * log(scale) - lgamma(shape) - (shape + 1.0) * log(x) - scale / x;
+}
+
+__device__ inline double block_sum(double v, double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < nw; w++) s += red[w];
+    return s;
+}
+
+// u' SigmaU^-1 u for the block matrix of src/utils.jl:17-33 (each block cov*11' + d*I), whole CTA cooperates
+__device__ inline double block_u_quad(const ModelDev& m, const double* u, double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double part = 0.0;
+    for (int o = warp; o < m.n_obj; o += nw) {
+        const int s0 = m.obj_start[o], cnt = m.obj_start[o + 1] - s0;
+        double s = 0.0;
+        for (int i = lane; i < cnt; i += 32) s += u[s0 + i];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        const double mean = s / cnt;
+        double dv = 0.0;
+        for (int i = lane; i < cnt; i += 32) { const double t = u[s0 + i] - mean; dv = fma(t, t, dv); }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) dv += __shfl_xor_sync(0xffffffffu, dv, off);
+        if (lane == 0) part += dv / m.dU + cnt * mean * mean / (m.dU + cnt * m.cov);
+    }
+    return block_sum(part, red);
+}
+
+// element (r, c) of the n x nU matrix the model's kernels see (src/model_likelihood.jl:7 + src/utils.jl:60-64)
+__device__ __forceinline__ void ueff_src(const ModelDev& m, int r, int c, int& a, int& b) {
+    if (m.u_layout_reference) { const long long f = (long long)r + (long long)c * m.n; a = (int)(f % m.nU); b = (int)(f / m.nU); }
+    else { a = c; b = r; }
+}
+
+// rebuild Ueff (or UeffP with U_k replaced by `repl`) for one chain
+__device__ inline void build_ueff(const ModelDev& m, const double* U, int k, const double* repl, double* out) {
+    const int total = m.n * m.nU;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int c = i / m.n, r = i - c * m.n;
+        int a, b;
+        ueff_src(m, r, c, a, b);
+        out[i] = (repl && a == k) ? repl[b] : U[(size_t)a * m.n + b];
+    }
+}
+
+__device__ inline void build_spec(const ModelDev& m, const ChainDev& c, int chain, int f, const double* Ubase, int ov_param,
+                                  double ov_val, RbfSpec* spec) {
+    const FactorDef& fd = m.fdef[f];
+    const double* theta = c.theta + (size_t)chain * m.n_params;
+    const double* Xm = m.has_xmodel ? c.Xmodel + (size_t)chain * m.n * m.nX : m.X;
+    for (int d = threadIdx.x; d < fd.D; d += blockDim.x) {
+        const int kind = fd.src_kind[d], idx = fd.src_idx[d];
+        spec->feat[d] = (kind == SRC_U) ? Ubase + (size_t)idx * m.n : (kind == SRC_X) ? Xm + (size_t)idx * m.n : m.T;
+        const int p = fd.ls_param[d];
+        const double ls = (p == ov_param) ? ov_val : theta[p];
+        spec->w[d] = 1.0 / (ls * ls);
+    }
+    if (threadIdx.x == 0) {
+        spec->D = fd.D;
+        spec->n = m.n;
+        spec->scale = (fd.scale_param == ov_param) ? ov_val : theta[fd.scale_param];
+        spec->noise = (fd.noise_param == ov_param) ? ov_val : theta[fd.noise_param];
+        const double* y = (fd.target_kind == TGT_XCOL) ? m.X + (size_t)fd.target_idx * m.n
+                          : (fd.target_kind == TGT_T)  ? m.T
+                          : (fd.target_kind == TGT_LOGIT) ? c.logitT + (size_t)chain * m.n : m.Y;
+        spec->y[0] = y; spec->y[1] = y;
+    }
+}
+
+__device__ __forceinline__ double logpdf_from(const FactorOut& o, int n) {
+    return (o.info == 0) ? -0.5 * (n * LOG_2PI + o.logdet + o.gram[0]) : -INFINITY;
+}
+
+// ------------------------------------------------------------------------------------------------ init (`generate`)
+__global__ void __launch_bounds__(256) init_chains_kernel(ModelDev m, ChainDev c) {
+    __shared__ double red[32];
+    const int chain = blockIdx.x;
+    const unsigned gchain = (unsigned)(m.chain0 + chain);
+    double* theta = c.theta + (size_t)chain * m.n_params;
+    for (int p = threadIdx.x; p < m.n_params; p += blockDim.x) theta[p] = nan("");
+    __syncthreads();
+    for (int s = threadIdx.x; s < m.n_sites; s += blockDim.x) {
+        const SiteDef sd = m.sites[s];
+        Stream st(m.seed, gchain, (uint32_t)sd.param, stream_b(TAG_INIT_PARAM, 0));
+        theta[sd.param] = st.inv_gamma(sd.pshape, sd.pscale);
+    }
+    __syncthreads();
+    for (int k = 0; k < m.nU; k++) {
+        const double un = theta[0];
+        Stream st(m.seed, gchain, (uint32_t)k, stream_b(TAG_INIT_VEC, 0));
+        double* u = c.U + ((size_t)chain * m.nU + k) * m.n;
+        const double su = sqrt(un), sc = sqrt(m.cov), sd = sqrt(m.dU);
+        for (int i = threadIdx.x; i < m.n; i += blockDim.x)
+            u[i] = su * (sc * st.normal_at(m.n + m.obj_of[i]) + sd * st.normal_at(i));
+    }
+    if (m.has_xmodel) {
+        for (int k = 0; k < m.nX; k++) {
+            Stream st(m.seed, gchain, (uint32_t)k, stream_b(TAG_INIT_XMODEL, 0));
+            double* x = c.Xmodel + ((size_t)chain * m.nX + k) * m.n;
+            for (int i = threadIdx.x; i < m.n; i += blockDim.x) x[i] = st.normal_at(i);
+        }
+    }
+    __syncthreads();
+    if (m.nU > 0) {
+        build_ueff(m, c.U + (size_t)chain * m.nU * m.n, -1, nullptr, c.Ueff + (size_t)chain * m.nU * m.n);
+        for (int k = 0; k < m.nU; k++) {
+            const double qv = block_u_quad(m, c.U + ((size_t)chain * m.nU + k) * m.n, red);
+            if (threadIdx.x == 0) c.q[(size_t)chain * m.nU + k] = qv;
+        }
+    }
+    if (threadIdx.x == 0) c.info[chain] = 0;
+}
+
+// recompute the derived per-chain quantities (Ueff, q) after the host overwrote theta/U (gpslc_sampler_set_state)
+__global__ void __launch_bounds__(256) refresh_chains_kernel(ModelDev m, ChainDev c) {
+    __shared__ double red[32];
+    const int chain = blockIdx.x;
+    if (m.nU > 0) {
+        build_ueff(m, c.U + (size_t)chain * m.nU * m.n, -1, nullptr, c.Ueff + (size_t)chain * m.nU * m.n);
+        for (int k = 0; k < m.nU; k++) {
+            const double qv = block_u_quad(m, c.U + ((size_t)chain * m.nU + k) * m.n, red);
+            if (threadIdx.x == 0) c.q[(size_t)chain * m.nU + k] = qv;
+        }
+    }
+    if (threadIdx.x == 0) c.info[chain] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------ factor evaluation
+// tasks = (chain from list or all chains) x (existing factors); writes lp / lpP
+__global__ void __launch_bounds__(FTHREADS, 2)
+eval_factors_kernel(ModelDev m, ChainDev c, const int* list, const unsigned int* n_list_dev, int n_all, const int* exist,
+                    int n_exist, int proposed, double* scratch, size_t slot_scratch, double* zbuf, size_t slot_z,
+                    unsigned int* counter) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FactorSmem& sm = *reinterpret_cast<FactorSmem*>(smem_raw);
+    __shared__ RbfSpec spec;
+    __shared__ unsigned int job;
+    factor_smem_init(sm);
+    Pipe pipe{0, 0};
+    const int NCB = ceil_div(m.n, NB);
+    double* my_scratch = scratch + (size_t)blockIdx.x * slot_scratch;
+    double* my_z = zbuf + (size_t)blockIdx.x * slot_z;
+    const unsigned int n_list = list ? *n_list_dev : (unsigned)n_all;
+    const unsigned int total = n_list * (unsigned)n_exist;
+    for (;;) {
+        if (threadIdx.x == 0) job = atomicAdd(counter, 1u);
+        __syncthreads();
+        const unsigned int t = job;
+        if (t >= total) break;
+        const int li = t / n_exist, f = exist[t - li * n_exist];
+        const int chain = list ? list[li] : li;
+        const double* Ubase = (proposed ? c.UeffP : c.Ueff) + (size_t)chain * m.nU * m.n;
+        build_spec(m, c, chain, f, Ubase, -1, 0.0, &spec);
+        __syncthreads();
+        RbfGen gen{&spec};
+        factor_run(gen, NCB, NCB, 1, my_scratch, my_z, sm, pipe);
+        if (threadIdx.x == 0) {
+            const FactorOut o = sm.out;
+            (proposed ? c.lpP : c.lp)[(size_t)chain * m.nF + f] = logpdf_from(o, m.n);
+            if (o.info != 0) {
+                if (proposed) atomicOr(&c.infoP[chain], 1);
+                else atomicMax(&c.info[chain], o.info);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ MH lanes
+// One task = (chain, lane): all single-site MH updates (src/proposal.jl:32-41 + Gen `mh`) of the
+// sites feeding one GP factor, for sweeps [j0, j1) of outer iteration `outer`.
+__global__ void __launch_bounds__(FTHREADS, 2)
+mh_lanes_kernel(ModelDev m, ChainDev c, const int* lane_order, int outer, int j0, int j1, double* scratch, size_t slot_scratch,
+                double* zbuf, size_t slot_z, unsigned int* counter) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FactorSmem& sm = *reinterpret_cast<FactorSmem*>(smem_raw);
+    __shared__ RbfSpec spec;
+    __shared__ unsigned int job;
+    __shared__ double s_new, s_part;
+    factor_smem_init(sm);
+    Pipe pipe{0, 0};
+    const int NCB = ceil_div(m.n, NB);
+    double* my_scratch = scratch + (size_t)blockIdx.x * slot_scratch;
+    double* my_z = zbuf + (size_t)blockIdx.x * slot_z;
+    const unsigned int total = (unsigned)m.n_chains * (unsigned)m.n_lanes;
+    for (;;) {
+        if (threadIdx.x == 0) job = atomicAdd(counter, 1u);
+        __syncthreads();
+        const unsigned int t = job;
+        if (t >= total) break;
+        // lanes in decreasing-work order, chains innermost: long lanes of every chain are scheduled first (LPT)
+        const int lane_id = lane_order[t / m.n_chains];
+        const int chain = t % m.n_chains;
+        const unsigned gchain = (unsigned)(m.chain0 + chain);
+        const int f = m.lane_factor[lane_id];
+        double* theta = c.theta + (size_t)chain * m.n_params;
+        const double* Ubase = c.Ueff + (size_t)chain * m.nU * m.n;
+        for (int j = j0; j < j1; j++) {
+            const uint32_t it = (uint32_t)(outer * m.nMH + j);
+            for (int si = m.lane_off[lane_id]; si < m.lane_off[lane_id + 1]; si++) {
+                const int s = m.lane_sites[si];
+                const SiteDef sd = m.sites[s];
+                if (threadIdx.x == 0) {
+                    const double cur = theta[sd.param];
+                    const double shape_f = cur * cur / m.drift + 2.0, scale_f = cur * (shape_f - 1.0);
+                    Stream st(m.seed, gchain, (uint32_t)s, stream_b(TAG_MH_PROP, it));
+                    const double nw = st.inv_gamma(shape_f, scale_f);
+                    const double fwd = ig_logpdf(nw, shape_f, scale_f);
+                    const double shape_b = nw * nw / m.drift + 2.0, scale_b = nw * (shape_b - 1.0);
+                    const double bwd = ig_logpdf(cur, shape_b, scale_b);
+                    const double dprior = ig_logpdf(nw, sd.pshape, sd.pscale) - ig_logpdf(cur, sd.pshape, sd.pscale);
+                    s_new = nw;
+                    s_part = dprior - fwd + bwd;
+                }
+                __syncthreads();
+                const double nw = s_new;
+                double dlik;
+                if (f >= 0) {
+                    build_spec(m, c, chain, f, Ubase, sd.param, nw, &spec);
+                    __syncthreads();
+                    RbfGen gen{&spec};
+                    factor_run(gen, NCB, NCB, 1, my_scratch, my_z, sm, pipe);
+                    dlik = 0.0;
+                } else {
+                    dlik = 0.0;
+                }
+                if (threadIdx.x == 0) {
+                    double lp_new = 0.0;
+                    if (f >= 0) {
+                        lp_new = logpdf_from(sm.out, m.n);
+                        dlik = lp_new - c.lp[(size_t)chain * m.nF + f];
+                    } else {
+                        // uNoise: only the nU terms log N(U_k; 0, uNoise*SigmaU) change (closed form, cached q_k)
+                        const double cur = theta[sd.param];
+                        for (int k = 0; k < m.nU; k++)
+                            dlik += -0.5 * (m.n * (log(nw) - log(cur)) + c.q[(size_t)chain * m.nU + k] * (1.0 / nw - 1.0 / cur));
+                    }
+                    const double alpha = s_part + dlik;
+                    Stream sa(m.seed, gchain, (uint32_t)s, stream_b(TAG_MH_ACC, it));
+                    const double u = sa.uniform();
+                    if (log(u) < alpha) {
+                        theta[sd.param] = nw;
+                        if (f >= 0) c.lp[(size_t)chain * m.nF + f] = lp_new;
+                        c.accepts[(size_t)chain * m.n_sites + s] += 1ull;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ ESS over U_k
+// ess[c][0..4] = log u, theta, theta_min, theta_max, next scalar-stream block
+__device__ inline void ess_make_proposal(const ModelDev& m, const ChainDev& c, int chain, int k, double th, double* red) {
+    const double* u = c.U + ((size_t)chain * m.nU + k) * m.n;
+    const double* nu = c.nu + (size_t)chain * m.n;
+    double* up = c.Uprop + (size_t)chain * m.n;
+    const double cs = cos(th), sn = sin(th);
+    for (int i = threadIdx.x; i < m.n; i += blockDim.x) up[i] = u[i] * cs + nu[i] * sn;
+    __syncthreads();
+    build_ueff(m, c.U + (size_t)chain * m.nU * m.n, k, up, c.UeffP + (size_t)chain * m.nU * m.n);
+    const double qv = block_u_quad(m, up, red);
+    if (threadIdx.x == 0) { c.qP[chain] = qv; c.infoP[chain] = 0; }
+}
+
+__global__ void __launch_bounds__(256) ess_begin_kernel(ModelDev m, ChainDev c, int k, uint32_t it) {
+    __shared__ double red[32];
+    __shared__ double s_th;
+    const int chain = blockIdx.x;
+    const unsigned gchain = (unsigned)(m.chain0 + chain);
+    const double un = c.theta[(size_t)chain * m.n_params + 0];
+    Stream sn(m.seed, gchain, (uint32_t)k, stream_b(TAG_ESS_NU, it));
+    double* nu = c.nu + (size_t)chain * m.n;
+    const double su = sqrt(un), sc = sqrt(m.cov), sd = sqrt(m.dU);
+    for (int i = threadIdx.x; i < m.n; i += blockDim.x)
+        nu[i] = su * (sc * sn.normal_at(m.n + m.obj_of[i]) + sd * sn.normal_at(i));
+    if (threadIdx.x == 0) {
+        Stream ss(m.seed, gchain, (uint32_t)k, stream_b(TAG_ESS_SCALAR, it));
+        double u, v;
+        ss.uniform_pair(u, v);
+        const double th = 2.0 * 3.14159265358979323846 * v;
+        double* e = c.ess + (size_t)chain * 8;
+        e[0] = log(u); e[1] = th; e[2] = th - 2.0 * 3.14159265358979323846; e[3] = th; e[4] = 1.0;
+        s_th = th;
+        c.active_a[chain] = chain;
+        if (chain == 0) { c.n_active[0] = gridDim.x; c.n_active[1] = 0; }
+    }
+    __syncthreads();
+    ess_make_proposal(m, c, chain, k, s_th, red);
+}
+
+__global__ void __launch_bounds__(256) ess_decide_kernel(ModelDev m, ChainDev c, int k, uint32_t it, const int* list_in,
+                                                         int* list_out, unsigned int* n_out, const int* exist, int n_exist) {
+    __shared__ double red[32];
+    __shared__ double s_th;
+    __shared__ int s_accept;
+    const int chain = list_in[blockIdx.x];
+    const unsigned gchain = (unsigned)(m.chain0 + chain);
+    double* e = c.ess + (size_t)chain * 8;
+    if (threadIdx.x == 0) {
+        double w = 0.0;
+        for (int i = 0; i < n_exist; i++) {
+            const int f = exist[i];
+            w += c.lpP[(size_t)chain * m.nF + f] - c.lp[(size_t)chain * m.nF + f];
+        }
+        // Gen's `elliptical_slice` compares the full `update` weight, which includes the N(0, uNoise*SigmaU) prior term
+        // at the sliced address; ess_rule 1 = textbook likelihood-only rule.
+        if (m.ess_rule == 0) w += -0.5 * (c.qP[chain] - c.q[(size_t)chain * m.nU + k]) / c.theta[(size_t)chain * m.n_params + 0];
+        if (c.infoP[chain] != 0) w = -INFINITY;
+        c.ess_evals[chain] += 1ull;
+        const bool acc = (w > e[0]);
+        s_accept = acc ? 1 : 0;
+        if (!acc) {
+            double th = e[1];
+            if (th < 0.0) e[2] = th; else e[3] = th;
+            Stream ss(m.seed, gchain, (uint32_t)k, stream_b(TAG_ESS_SCALAR, it));
+            ss.block = (uint32_t)e[4];
+            th = e[2] + (e[3] - e[2]) * ss.uniform();
+            e[4] += 1.0;
+            e[1] = th;
+            s_th = th;
+            const unsigned int pos = atomicAdd(n_out, 1u);
+            list_out[pos] = chain;
+        }
+    }
+    __syncthreads();
+    if (s_accept) {
+        double* u = c.U + ((size_t)chain * m.nU + k) * m.n;
+        const double* up = c.Uprop + (size_t)chain * m.n;
+        for (int i = threadIdx.x; i < m.n; i += blockDim.x) u[i] = up[i];
+        double* ue = c.Ueff + (size_t)chain * m.nU * m.n;
+        const double* uep = c.UeffP + (size_t)chain * m.nU * m.n;
+        for (int i = threadIdx.x; i < m.n * m.nU; i += blockDim.x) ue[i] = uep[i];
+        for (int i = threadIdx.x; i < n_exist; i += blockDim.x) {
+            const int f = exist[i];
+            c.lp[(size_t)chain * m.nF + f] = c.lpP[(size_t)chain * m.nF + f];
+        }
+        if (threadIdx.x == 0) c.q[(size_t)chain * m.nU + k] = c.qP[chain];
+    } else {
+        ess_make_proposal(m, c, chain, k, s_th, red);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ sample record
+__global__ void record_kernel(ModelDev m, ChainDev c, double* samples, int slot) {
+    const int chain = blockIdx.x;
+    double* dst = samples + ((size_t)slot * m.n_chains + chain) * m.stride;
+    const double* theta = c.theta + (size_t)chain * m.n_params;
+    for (int i = threadIdx.x; i < m.n_params; i += blockDim.x) dst[i] = theta[i];
+    dst += m.n_params;
+    const int nu = m.nU * m.n;
+    const double* U = c.U + (size_t)chain * nu;
+    for (int i = threadIdx.x; i < nu; i += blockDim.x) dst[i] = U[i];
+    dst += nu;
+    if (m.binary) {
+        const double* lt = c.logitT + (size_t)chain * m.n;
+        for (int i = threadIdx.x; i < m.n; i += blockDim.x) dst[i] = lt[i];
+        dst += m.n;
+    }
+    if (m.has_xmodel) {
+        const double* xm = c.Xmodel + (size_t)chain * m.n * m.nX;
+        for (int i = threadIdx.x; i < m.n * m.nX; i += blockDim.x) dst[i] = xm[i];
+    }
+}
+
+// ================================================================================================ host side
+
+template <class T>
+static int dev_alloc(Sampler* s, T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    GP_CUDA(s->ctx, cudaMalloc((void**)p, count * sizeof(T)));
+    s->owned.push_back((void*)*p);
+    return GPSLC_OK;
+}
+template <class T>
+static int dev_upload(Sampler* s, T** p, const std::vector<T>& v) {
+    GP_TRY(dev_alloc(s, p, v.size()));
+    if (!v.empty()) GP_CUDA(s->ctx, cudaMemcpyAsync(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s->ctx->stream));
+    return GPSLC_OK;
+}
+
+static int param_idx(int nX, int nU, const char* name, int i, int j) {
+    std::string s(name);
+    if (s == "uNoise") return 0;
+    if (s == "tNoise") return 1;
+    if (s == "yNoise") return 2;
+    if (s == "tyLS") return 3;
+    if (s == "tScale") return 4;
+    if (s == "yScale") return 5;
+    if (s == "xNoise") return 6 + i;
+    if (s == "xScale") return 6 + nX + i;
+    if (s == "xtLS") return 6 + 2 * nX + i;
+    if (s == "xyLS") return 6 + 3 * nX + i;
+    if (s == "utLS") return 6 + 4 * nX + i;
+    if (s == "uyLS") return 6 + 4 * nX + nU + i;
+    return 6 + 4 * nX + 2 * nU + i * nX + j;  // uxLS
+}
+
+void sampler_free(Sampler* s) {
+    if (!s) return;
+    cudaStreamSynchronize(s->ctx->stream);
+    for (void* p : s->owned) cudaFree(p);
+    if (s->samples) cudaFree(s->samples);
+    delete s;
+}
+
+// Build every table. data pointers are host pointers (loc==0) or device pointers (loc==1).
+int sampler_create(Ctx* ctx, int loc, int n, int nX, int nU, int binary, const double* X, const double* T, const double* Y,
+                   int n_obj, const int* obj_counts, double eps, double cov, const double* pshape, const double* pscale,
+                   double drift, int nMH, int nES, int n_chains, unsigned long long seed, int chain_offset, int u_layout_mode,
+                   int ess_rule, int observe_x, Sampler** out) {
+    *out = nullptr;
+    if (n <= 0 || nX < 0 || nU < 0 || n_chains <= 0 || !T || !Y || (nX > 0 && !X)) return ctx->fail(GPSLC_ERR_ARG, "sampler_create: bad argument");
+    if (nU + nX + 1 > DMAX) return ctx->fail(GPSLC_ERR_UNSUPPORTED, "sampler_create: nU + nX + 1 exceeds DMAX");
+    if (binary) return ctx->fail(GPSLC_ERR_UNSUPPORTED, "sampler_create: binary treatment is not implemented in this build");
+    const bool has_u = nU > 0, has_x = nX > 0;
+    if (has_u) {
+        if (n_obj <= 0 || !obj_counts) return ctx->fail(GPSLC_ERR_ARG, "sampler_create: nU > 0 needs the object counts of SigmaU");
+        long long tot = 0;
+        for (int o = 0; o < n_obj; o++) { if (obj_counts[o] <= 0) return ctx->fail(GPSLC_ERR_ARG, "sampler_create: non-positive object count"); tot += obj_counts[o]; }
+        if (tot != n) return ctx->fail(GPSLC_ERR_ARG, "sampler_create: object counts do not sum to n");
+        if (!((1.0 + eps) - cov > 0.0) || !(cov >= 0.0)) return ctx->fail(GPSLC_ERR_ARG, "sampler_create: SigmaU needs 0 <= cov < 1+eps");
+    }
+    GP_CUDA(ctx, cudaSetDevice(ctx->device));
+    Sampler* s = new Sampler();
+    s->ctx = ctx;
+    ModelDev& m = s->m;
+    m.n = n; m.nU = nU; m.nX = nX; m.nF = nX + 2; m.binary = binary;
+    m.n_params = 6 + 4 * nX + 2 * nU + nU * nX;
+    m.has_xmodel = (!has_u && has_x && !observe_x) ? 1 : 0;
+    m.stride = m.n_params + nU * n + (binary ? n : 0) + (m.has_xmodel ? n * nX : 0);
+    m.u_layout_reference = (u_layout_mode == 0) ? 1 : 0;
+    m.ess_rule = ess_rule;
+    m.eps = eps; m.cov = cov; m.dU = (1.0 + eps) - cov; m.drift = drift;
+    m.seed = seed; m.chain0 = chain_offset; m.n_chains = n_chains;
+    m.nMH = (!has_u && !has_x) ? 1 : nMH;   // inference.jl:157-160: three sites once per outer iteration
+    m.nES = nES;
+    m.n_obj = has_u ? n_obj : 0;
+
+    // ---- factor table (src/model_likelihood.jl)
+    s->h_fdef.assign(m.nF, FactorDef{});
+    auto uxls_param = [&](int k, int c) {  // lengthscale of U column c in the X_k kernel (model_prior.jl:110, App. B1)
+        if (m.u_layout_reference) { const long long f = (long long)k + (long long)c * nX; return param_idx(nX, nU, "uxLS", (int)(f % nU), (int)(f / nU)); }
+        return param_idx(nX, nU, "uxLS", c, k);
+    };
+    for (int f = 0; f < m.nF; f++) {
+        FactorDef& fd = s->h_fdef[f];
+        int D = 0;
+        if (f < nX) {
+            fd.exists = has_u;
+            for (int c = 0; c < nU; c++) { fd.src_kind[D] = SRC_U; fd.src_idx[D] = c; fd.ls_param[D] = uxls_param(f, c); D++; }
+            fd.scale_param = param_idx(nX, nU, "xScale", f, 0); fd.noise_param = param_idx(nX, nU, "xNoise", f, 0);
+            fd.target_kind = TGT_XCOL; fd.target_idx = f;
+        } else if (f == nX) {
+            fd.exists = has_u || has_x;
+            for (int c = 0; c < nU; c++) { fd.src_kind[D] = SRC_U; fd.src_idx[D] = c; fd.ls_param[D] = param_idx(nX, nU, "utLS", c, 0); D++; }
+            for (int k = 0; k < nX; k++) { fd.src_kind[D] = SRC_X; fd.src_idx[D] = k; fd.ls_param[D] = param_idx(nX, nU, "xtLS", k, 0); D++; }
+            fd.scale_param = 4; fd.noise_param = 1;
+            fd.target_kind = binary ? TGT_LOGIT : TGT_T; fd.target_idx = 0;
+        } else {
+            fd.exists = 1;
+            for (int c = 0; c < nU; c++) { fd.src_kind[D] = SRC_U; fd.src_idx[D] = c; fd.ls_param[D] = param_idx(nX, nU, "uyLS", c, 0); D++; }
+            for (int k = 0; k < nX; k++) { fd.src_kind[D] = SRC_X; fd.src_idx[D] = k; fd.ls_param[D] = param_idx(nX, nU, "xyLS", k, 0); D++; }
+            fd.src_kind[D] = SRC_T; fd.src_idx[D] = 0; fd.ls_param[D] = 3; D++;
+            fd.scale_param = 5; fd.noise_param = 2;
+            fd.target_kind = TGT_Y; fd.target_idx = 0;
+        }
+        fd.D = D;
+    }
+    // ---- MH sites in sweep order (src/inference.jl:23-44, 76-87, 127-137, 158-160)
+    auto add_site = [&](const char* name, int i, int j, int fam, int factor) {
+        SiteDef sd; sd.param = param_idx(nX, nU, name, i, j); sd.factor = factor; sd.pshape = pshape[fam]; sd.pscale = pscale[fam];
+        s->h_sites.push_back(sd);
+    };
+    const int FT = nX, FY = nX + 1;
+    if (has_u) add_site("uNoise", 0, 0, P_UNOISE, -1);
+    if (has_u || has_x) add_site("tNoise", 0, 0, P_TNOISE, FT);
+    add_site("yNoise", 0, 0, P_YNOISE, FY);
+    add_site("tyLS", 0, 0, P_TYLS, FY);
+    if (has_u) for (int k = 0; k < nU; k++) {
+        add_site("utLS", k, 0, P_UTLS, FT);
+        add_site("uyLS", k, 0, P_UYLS, FY);
+        for (int l = 0; l < nX; l++) {
+            const int fx = m.u_layout_reference ? (int)(((long long)k + (long long)l * nU) % nX) : l;
+            add_site("uxLS", k, l, P_UXLS, fx);
+        }
+    }
+    if (has_x) for (int k = 0; k < nX; k++) {
+        if (has_u) add_site("xNoise", k, 0, P_XNOISE, k);
+        add_site("xtLS", k, 0, P_XTLS, FT);
+        add_site("xyLS", k, 0, P_XYLS, FY);
+        if (has_u) add_site("xScale", k, 0, P_XSCALE, k);
+    }
+    if (has_u || has_x) add_site("tScale", 0, 0, P_TSCALE, FT);
+    add_site("yScale", 0, 0, P_YSCALE, FY);
+    m.n_sites = (int)s->h_sites.size();
+    // ---- lanes: sites grouped by the factor they feed (-1 = uNoise lane)
+    {
+        std::vector<int> keys;
+        for (auto& sd : s->h_sites) { bool seen = false; for (int k : keys) seen |= (k == sd.factor); if (!seen) keys.push_back(sd.factor); }
+        s->h_lane_off.push_back(0);
+        for (int key : keys) {
+            for (int i = 0; i < m.n_sites; i++) if (s->h_sites[i].factor == key) s->h_lane_sites.push_back(i);
+            s->h_lane_off.push_back((int)s->h_lane_sites.size());
+            s->h_lane_factor.push_back(key);
+        }
+        m.n_lanes = (int)keys.size();
+        s->lane_task_order.resize(m.n_lanes);
+        for (int l = 0; l < m.n_lanes; l++) s->lane_task_order[l] = l;
+        auto work = [&](int l) { return (s->h_lane_factor[l] < 0 ? 0 : 1000) + (s->h_lane_off[l + 1] - s->h_lane_off[l]); };
+        std::sort(s->lane_task_order.begin(), s->lane_task_order.end(), [&](int a, int b) { return work(a) > work(b); });
+    }
+    std::vector<int> exist;
+    for (int f = 0; f < m.nF; f++) if (s->h_fdef[f].exists) exist.push_back(f);
+    s->n_exist = (int)exist.size();
+
+    // ---- uploads
+    int rc = GPSLC_OK;
+    auto up_data = [&](const double* src, size_t count, const double** dst) -> int {
+        if (!src || count == 0) { *dst = nullptr; return GPSLC_OK; }
+        if (loc == 1) { *dst = src; return GPSLC_OK; }
+        double* d;
+        GP_TRY(dev_alloc(s, &d, count));
+        GP_CUDA(ctx, cudaMemcpyAsync(d, src, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        *dst = d;
+        return GPSLC_OK;
+    };
+#define S_TRY(expr) do { rc = (expr); if (rc) { sampler_free(s); return rc; } } while (0)
+    S_TRY(up_data(X, (size_t)n * nX, &m.X));
+    S_TRY(up_data(T, n, &m.T));
+    S_TRY(up_data(Y, n, &m.Y));
+    {
+        std::vector<int> start(m.n_obj + 1, 0), of(n, 0);
+        for (int o = 0; o < m.n_obj; o++) { start[o + 1] = start[o] + obj_counts[o]; for (int i = start[o]; i < start[o + 1]; i++) of[i] = o; }
+        int *d1, *d2;
+        S_TRY(dev_upload(s, &d1, start)); S_TRY(dev_upload(s, &d2, of));
+        m.obj_start = d1; m.obj_of = d2;
+    }
+    { FactorDef* d; S_TRY(dev_upload(s, &d, s->h_fdef)); m.fdef = d; }
+    { SiteDef* d; S_TRY(dev_upload(s, &d, s->h_sites)); m.sites = d; }
+    { int* d; S_TRY(dev_upload(s, &d, s->h_lane_sites)); m.lane_sites = d; }
+    { int* d; S_TRY(dev_upload(s, &d, s->h_lane_off)); m.lane_off = d; }
+    { int* d; S_TRY(dev_upload(s, &d, s->h_lane_factor)); m.lane_factor = d; }
+    S_TRY(dev_upload(s, &s->d_lane_order, s->lane_task_order));
+    S_TRY(dev_upload(s, &s->d_exist, exist));
+    // ---- chain state
+    ChainDev& c = s->c;
+    const size_t C = n_chains;
+    S_TRY(dev_alloc(s, &c.theta, C * m.n_params));
+    S_TRY(dev_alloc(s, &c.U, C * nU * n));
+    S_TRY(dev_alloc(s, &c.Ueff, C * nU * n));
+    S_TRY(dev_alloc(s, &c.UeffP, C * nU * n));
+    S_TRY(dev_alloc(s, &c.Uprop, C * n));
+    S_TRY(dev_alloc(s, &c.nu, C * n));
+    S_TRY(dev_alloc(s, &c.lp, C * m.nF));
+    S_TRY(dev_alloc(s, &c.lpP, C * m.nF));
+    S_TRY(dev_alloc(s, &c.q, C * (nU > 0 ? nU : 1)));
+    S_TRY(dev_alloc(s, &c.qP, C));
+    S_TRY(dev_alloc(s, &c.ess, C * 8));
+    S_TRY(dev_alloc(s, &c.logitT, binary ? C * n : 1));
+    S_TRY(dev_alloc(s, &c.Xmodel, m.has_xmodel ? C * n * nX : 1));
+    S_TRY(dev_alloc(s, &c.info, C));
+    S_TRY(dev_alloc(s, &c.infoP, C));
+    S_TRY(dev_alloc(s, &c.active_a, C));
+    S_TRY(dev_alloc(s, &c.active_b, C));
+    S_TRY(dev_alloc(s, &c.n_active, 2));
+    S_TRY(dev_alloc(s, &c.accepts, C * m.n_sites));
+    S_TRY(dev_alloc(s, &c.ess_evals, C));
+    cudaMemsetAsync(c.lp, 0, C * m.nF * sizeof(double), ctx->stream);
+    cudaMemsetAsync(c.lpP, 0, C * m.nF * sizeof(double), ctx->stream);
+    cudaMemsetAsync(c.accepts, 0, C * m.n_sites * sizeof(unsigned long long), ctx->stream);
+    cudaMemsetAsync(c.ess_evals, 0, C * sizeof(unsigned long long), ctx->stream);
+    cudaMemsetAsync(c.info, 0, C * sizeof(int), ctx->stream);
+    cudaMemsetAsync(c.infoP, 0, C * sizeof(int), ctx->stream);
+    const int NCB = ceil_div(n, NB);
+    S_TRY(ensure_workspace(ctx, NCB, NCB));
+#undef S_TRY
+    *out = s;
+    return GPSLC_OK;
+}
+
+static int launch_eval(Sampler* s, const int* list, const unsigned int* n_list_dev, int n_list_host, int proposed) {
+    Ctx* ctx = s->ctx;
+    if (s->n_exist == 0 || n_list_host == 0) return GPSLC_OK;
+    GP_CUDA(ctx, cudaFuncSetAttribute(eval_factors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
+    GP_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, sizeof(unsigned int), ctx->stream));
+    const long long tasks = (long long)n_list_host * s->n_exist;
+    const int grid = (int)(tasks < ctx->slots ? tasks : ctx->slots);
+    eval_factors_kernel<<<grid, FTHREADS, sizeof(FactorSmem), ctx->stream>>>(s->m, s->c, list, n_list_dev, s->m.n_chains, s->d_exist,
+                                                                           s->n_exist, proposed, ctx->scratch, ctx->slot_scratch_d,
+                                                                           ctx->zbuf, ctx->slot_z_d, ctx->counter);
+    ctx->launches++;
+    GP_CUDA(ctx, cudaGetLastError());
+    return GPSLC_OK;
+}
+
+// `generate`: prior draws + initial factor log-densities. A non-PD initial factor is an error like the reference's
+// PosDefException.
+int sampler_init(Sampler* s) {
+    Ctx* ctx = s->ctx;
+    init_chains_kernel<<<s->m.n_chains, 256, 0, ctx->stream>>>(s->m, s->c);
+    ctx->launches++;
+    GP_CUDA(ctx, cudaGetLastError());
+    GP_TRY(launch_eval(s, nullptr, nullptr, s->m.n_chains, 0));
+    std::vector<int> info(s->m.n_chains);
+    GP_CUDA(ctx, cudaMemcpyAsync(info.data(), s->c.info, info.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < info.size(); i++)
+        if (info[i] != 0) return ctx->fail(GPSLC_ERR_NOT_PD, "initial state: covariance not positive definite (chain " + std::to_string(i) + ", minor " + std::to_string(info[i]) + ")");
+    s->outer_done = 0; s->sweeps_done = 0;
+    return GPSLC_OK;
+}
+
+// overwrite chain state from packed records [C][stride] (theta | U | ...) and recompute caches
+int sampler_set_state(Sampler* s, int loc, const double* packed) {
+    Ctx* ctx = s->ctx;
+    const ModelDev& m = s->m;
+    const cudaMemcpyKind kind = loc == 1 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    GP_CUDA(ctx, cudaMemcpy2DAsync(s->c.theta, m.n_params * sizeof(double), packed, m.stride * sizeof(double), m.n_params * sizeof(double), m.n_chains, kind, ctx->stream));
+    if (m.nU > 0)
+        GP_CUDA(ctx, cudaMemcpy2DAsync(s->c.U, (size_t)m.nU * m.n * sizeof(double), packed + m.n_params, m.stride * sizeof(double), (size_t)m.nU * m.n * sizeof(double), m.n_chains, kind, ctx->stream));
+    if (m.has_xmodel)
+        GP_CUDA(ctx, cudaMemcpy2DAsync(s->c.Xmodel, (size_t)m.nX * m.n * sizeof(double), packed + m.n_params + m.nU * m.n + (m.binary ? m.n : 0), m.stride * sizeof(double), (size_t)m.nX * m.n * sizeof(double), m.n_chains, kind, ctx->stream));
+    refresh_chains_kernel<<<m.n_chains, 256, 0, ctx->stream>>>(s->m, s->c);
+    ctx->launches++;
+    GP_CUDA(ctx, cudaGetLastError());
+    GP_TRY(launch_eval(s, nullptr, nullptr, m.n_chains, 0));
+    GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GPSLC_OK;
+}
+
+int sampler_mh(Sampler* s, int outer, int j0, int j1) {
+    Ctx* ctx = s->ctx;
+    if (j1 <= j0) return GPSLC_OK;
+    GP_CUDA(ctx, cudaFuncSetAttribute(mh_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
+    GP_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, sizeof(unsigned int), ctx->stream));
+    const long long tasks = (long long)s->m.n_chains * s->m.n_lanes;
+    const int grid = (int)(tasks < ctx->slots ? tasks : ctx->slots);
+    mh_lanes_kernel<<<grid, FTHREADS, sizeof(FactorSmem), ctx->stream>>>(s->m, s->c, s->d_lane_order, outer, j0, j1, ctx->scratch,
+                                                                       ctx->slot_scratch_d, ctx->zbuf, ctx->slot_z_d, ctx->counter);
+    ctx->launches++;
+    GP_CUDA(ctx, cudaGetLastError());
+    return GPSLC_OK;
+}
+
+// one elliptical-slice update of U_k for every chain (src/inference.jl:50-54): host loop over shrink rounds
+int sampler_ess_u(Sampler* s, int k, uint32_t it) {
+    Ctx* ctx = s->ctx;
+    const ModelDev& m = s->m;
+    ess_begin_kernel<<<m.n_chains, 256, 0, ctx->stream>>>(s->m, s->c, k, it);
+    ctx->launches++;
+    GP_CUDA(ctx, cudaGetLastError());
+    int cur = 0;
+    unsigned int n_act = (unsigned)m.n_chains;
+    while (n_act > 0) {
+        int* list_in = cur == 0 ? s->c.active_a : s->c.active_b;
+        int* list_out = cur == 0 ? s->c.active_b : s->c.active_a;
+        GP_TRY(launch_eval(s, list_in, s->c.n_active + cur, (int)n_act, 1));
+        GP_CUDA(ctx, cudaMemsetAsync(s->c.n_active + (1 - cur), 0, sizeof(unsigned int), ctx->stream));
+        ess_decide_kernel<<<n_act, 256, 0, ctx->stream>>>(s->m, s->c, k, it, list_in, list_out, s->c.n_active + (1 - cur), s->d_exist, s->n_exist);
+        ctx->launches++;
+        GP_CUDA(ctx, cudaGetLastError());
+        cur = 1 - cur;
+        GP_CUDA(ctx, cudaMemcpyAsync(&n_act, s->c.n_active + cur, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+        GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return GPSLC_OK;
+}
+
+int sampler_reserve_samples(Sampler* s, int n_outer_total) {
+    Ctx* ctx = s->ctx;
+    if (n_outer_total <= s->samples_cap) return GPSLC_OK;
+    double* nw = nullptr;
+    const size_t per = (size_t)s->m.n_chains * s->m.stride;
+    GP_CUDA(ctx, cudaMalloc(&nw, per * n_outer_total * sizeof(double)));
+    if (s->samples) {
+        GP_CUDA(ctx, cudaMemcpyAsync(nw, s->samples, per * s->outer_done * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(s->samples);
+    }
+    s->samples = nw;
+    s->samples_cap = n_outer_total;
+    return GPSLC_OK;
+}
+
+// run `n_outer` more outer iterations (MH sweeps + ESS passes + record)
+int sampler_run(Sampler* s, int n_outer) {
+    Ctx* ctx = s->ctx;
+    const ModelDev& m = s->m;
+    GP_TRY(sampler_reserve_samples(s, s->outer_done + n_outer));
+    for (int it = 0; it < n_outer; it++) {
+        const int i = s->outer_done;
+        GP_TRY(sampler_mh(s, i, s->sweeps_done, m.nMH));
+        s->sweeps_done = 0;
+        if (m.nU > 0) {
+            for (int j = 0; j < m.nES; j++)
+                for (int k = 0; k < m.nU; k++) GP_TRY(sampler_ess_u(s, k, (uint32_t)(i * m.nES + j)));
+        }
+        record_kernel<<<m.n_chains, 256, 0, ctx->stream>>>(s->m, s->c, s->samples, i);
+        ctx->launches++;
+        GP_CUDA(ctx, cudaGetLastError());
+        s->outer_done++;
+    }
+    return GPSLC_OK;
+}
+
+// bench/diagnostic stepping: `count` MH sweeps of every chain without ESS or recording; RNG iteration indices keep
+// advancing so no stream is reused
+int sampler_mh_sweeps(Sampler* s, int count) {
+    GP_TRY(sampler_mh(s, s->outer_done, s->sweeps_done, s->sweeps_done + count));
+    s->sweeps_done += count;
+    return GPSLC_OK;
+}
+
+int sampler_ess_pass(Sampler* s, int pass_index) {
+    for (int k = 0; k < s->m.nU; k++) GP_TRY(sampler_ess_u(s, k, (uint32_t)(s->outer_done * s->m.nES + pass_index)));
+    return GPSLC_OK;
+}
+
+int sampler_get_state(Sampler* s, double* dev_out /* [C][stride] device */) {
+    record_kernel<<<s->m.n_chains, 256, 0, s->ctx->stream>>>(s->m, s->c, dev_out, 0);
+    s->ctx->launches++;
+    GP_CUDA(s->ctx, cudaGetLastError());
+    return GPSLC_OK;
+}
+
+}  // namespace gpslc

@@ -82,6 +82,81 @@ int gpslc_rbf_logpdf(gpslc_ctx* ctx, int loc, int n, int batch, int D, const dou
                      const double* ls, const double* scale, const double* noise, const double* y, int y_shared,
                      double* logpdf, double* logdet, double* quad, int* info);
 
+/* ---- L3: the many-chain posterior sampler ------------------------------------------------------------------- */
+
+/* Observed data + confounder structure: the fields SigmaU, obj, X, T, Y of GPSLCObject (src/types.jl:249-258).
+ * SigmaU is passed as the object counts generateSigmaU (src/utils.jl:17-33) was built from, plus its eps/cov
+ * (priorparams["sigmaUNoise"], ["sigmaUCov"]); the library uses the closed form of that block matrix. */
+typedef struct {
+    int n;                 /* individuals */
+    int nX;                /* covariates; 0 == `X === nothing` */
+    int nU;                /* latent confounder dimensions (hyperparams.nU); 0 == `nothing` (no SigmaU) */
+    int binary;            /* 1 when T is Vector{Bool} */
+    const double* X;       /* n x nX column-major, or NULL */
+    const double* T;       /* n (0.0/1.0 when binary) */
+    const double* Y;       /* n */
+    int n_obj;             /* number of objects (blocks of SigmaU) */
+    const int* obj_counts; /* their sizes, in row order (rows sorted by obj as prepareData does, src/data.jl:25) */
+    double sigma_u_eps;    /* 1e-13 by default (src/hyperparameters.jl:66) */
+    double sigma_u_cov;    /* 1.0 by default  (src/hyperparameters.jl:67) */
+} gpslc_data;
+
+/* InvGamma(shape, scale) priors of src/hyperparameters.jl:39-65 in the order
+ * uNoise, xNoise, tNoise, yNoise, xScale, tScale, yScale, uxLS, utLS, xtLS, uyLS, xyLS, tyLS; and the MH drift. */
+typedef struct {
+    double shape[13];
+    double scale[13];
+    double drift;
+} gpslc_prior;
+
+typedef struct {
+    int nOuter, nMHInner, nESInner; /* HyperParameters (src/types.jl:22-30) */
+    int n_chains;                   /* independent chains run by this call (the reference runs 1) */
+    uint64_t seed;                  /* Philox key */
+    int chain_offset;               /* global id of chain 0 (multi-GPU sharding keeps streams independent of the split) */
+    int u_layout_mode;              /* 0: reference toMatrix interleave (identity when nU == 1); 1: column-wise */
+    int ess_rule;                   /* 0: Gen's joint-weight elliptical_slice test; 1: likelihood only */
+    int observe_x;                  /* no-U models: 0 = reference behaviour (X never observed, App. B3), 1 = condition on X */
+} gpslc_opts;
+
+typedef struct gpslc_sampler gpslc_sampler;
+
+/* Builds the model tables, uploads the data and performs Gen `generate` (src/inference.jl:20,73,123,156,189,261,321,370):
+ * every chain's hyperparameters are drawn from their priors and U_k ~ N(0, uNoise*SigmaU). Fails with
+ * GPSLC_ERR_NOT_PD if an initial covariance is not positive definite (the reference throws PosDefException). */
+int gpslc_sampler_create(gpslc_ctx* ctx, int loc, const gpslc_data* data, const gpslc_prior* prior, const gpslc_opts* opts,
+                         gpslc_sampler** out);
+void gpslc_sampler_destroy(gpslc_sampler* s);
+/* packed sample layout: [uNoise tNoise yNoise tyLS tScale yScale | xNoise[nX] | xScale[nX] | xtLS[nX] |
+ * xyLS[nX] | utLS[nU] | uyLS[nU] | uxLS[nU*nX, i-major] | U[nU*n, i-major] | logitT[n] if binary | Xmodel[n*nX] if any];
+ * unused hyperparameters are NaN. n_params = length of the hyperparameter part; stride = record length. */
+int gpslc_sampler_layout(const gpslc_sampler* s, int* n_params, int* stride, int* n_sites, int* n_factors);
+/* Run n_outer more outer iterations of `Posterior` (src/inference.jl:21-57): nMHInner MH sweeps, nESInner elliptical
+ * slice passes over U_1..U_nU, then record the sample. */
+int gpslc_sampler_run(gpslc_sampler* s, int n_outer);
+/* Stepping entry points used by bench.py: `count` MH sweeps of every chain (one sweep = the body of the
+ * `for j = 1:nMHInner` loop, src/inference.jl:22-45) / one ESS pass over all U_k. */
+int gpslc_sampler_mh_sweeps(gpslc_sampler* s, int count);
+int gpslc_sampler_ess_pass(gpslc_sampler* s, int pass_index);
+/* samples recorded so far: [outer_done][n_chains][stride] */
+int gpslc_sampler_get_samples(gpslc_sampler* s, int loc, double* out, int* outer_done);
+/* device pointer of the same buffer (valid until the next gpslc_sampler_run), for consumers that stay on the GPU */
+const double* gpslc_sampler_samples_device(gpslc_sampler* s);
+int gpslc_sampler_get_state(gpslc_sampler* s, int loc, double* packed /* [n_chains][stride] */);
+int gpslc_sampler_set_state(gpslc_sampler* s, int loc, const double* packed);
+/* cached log-joint pieces of the current state: log N(.) of every GP factor [n_chains][nX+2] (X_1..X_nX, T, Y; entries of
+ * factors that do not exist in the model variant are 0) and U_k' SigmaU^-1 U_k [n_chains][nU]. Parity layer for
+ * the log-joint of src/model.jl:11-130. */
+int gpslc_sampler_get_terms(gpslc_sampler* s, double* factor_logpdf, double* u_quad);
+/* accepted MH moves per (chain, site) in sweep order, and elliptical-slice model evaluations per chain */
+int gpslc_sampler_get_stats(gpslc_sampler* s, unsigned long long* accepts, unsigned long long* ess_evals);
+
+/* One-shot form, the body of `Posterior(priorparams, X, T, Y, nU, nOuter, nMHInner, nESInner)`
+ * (src/inference.jl:4-379, called from samplePosterior, src/driver.jl:59-69) for n_chains chains with host buffers:
+ * samples_out [nOuter][n_chains][stride]; accepts/ess_evals may be NULL. */
+int gpslc_posterior(gpslc_ctx* ctx, const gpslc_data* data, const gpslc_prior* prior, const gpslc_opts* opts,
+                    double* samples_out, unsigned long long* accepts, unsigned long long* ess_evals);
+
 #ifdef __cplusplus
 }
 #endif
