@@ -307,3 +307,77 @@ int gpslc_posterior(gpslc_ctx* h, const gpslc_data* d, const gpslc_prior* p, con
 }
 
 }  // extern "C"
+
+// ================================================================================================ estimation
+#include "est.cuh"
+namespace gpslc {
+int launch_ite(Ctx*, const EstArgs&);
+int launch_sate(Ctx*, const EstArgs&);
+}
+
+static int est_common(gpslc_ctx* h, int loc, const gpslc_data* d, const double* samples, int n_outer, int n_chains, int stride,
+                      const int* ret_idx, int R, const double* doT, int n_doT, double jitter, int spp, uint64_t seed,
+                      int chain_offset, int var_as_std, bool sate, double* o1, double* o2, double* o3, int* info) {
+    if (!h) return GPSLC_ERR_ARG;
+    Ctx* ctx = &h->c;
+    if (!d || !samples || !ret_idx || !doT || d->n <= 0 || R < 0 || n_doT < 0 || n_chains <= 0 || spp < 0)
+        return ctx->fail(GPSLC_ERR_ARG, "gpslc_ite/sate: bad argument");
+    const int n = d->n, nX = d->nX, nU = d->nU;
+    const int n_params = 6 + 4 * nX + 2 * nU + nU * nX;
+    if (stride < n_params + nU * n) return ctx->fail(GPSLC_ERR_ARG, "gpslc_ite/sate: stride too small for the packed layout");
+    if (nU + nX + 1 > DMAX) return ctx->fail(GPSLC_ERR_UNSUPPORTED, "gpslc_ite/sate: nU + nX + 1 exceeds DMAX");
+    if (R == 0 || n_doT == 0) return GPSLC_OK;
+    GP_CUDA(ctx, cudaSetDevice(ctx->device));
+    // ret_idx / doT are tiny host arrays in either mode
+    for (int r = 0; r < R; r++)
+        if (ret_idx[r] < 0 || ret_idx[r] >= n_outer) return ctx->fail(GPSLC_ERR_ARG, "gpslc_ite/sate: retained index out of range");
+    Staged<double> dX(ctx), dT(ctx), dY(ctx), dS(ctx), dDo(ctx), d1(ctx), d2(ctx), d3(ctx);
+    Staged<int> dRet(ctx), dInfo(ctx);
+    GP_TRY(dX.in(loc, d->X, (size_t)n * nX));
+    GP_TRY(dT.in(loc, d->T, n));
+    GP_TRY(dY.in(loc, d->Y, n));
+    GP_TRY(dS.in(loc, samples, (size_t)n_outer * n_chains * stride));
+    GP_TRY(dRet.in(0, ret_idx, R));
+    GP_TRY(dDo.in(0, doT, n_doT));
+    const size_t tasks = (size_t)n_doT * n_chains * R;
+    EstArgs a{};
+    a.n = n; a.nX = nX; a.nU = nU; a.n_params = n_params; a.stride = stride;
+    a.X = dX.d; a.T = dT.d; a.Y = dY.d; a.samples = dS.d; a.n_chains = n_chains; a.ret_idx = dRet.d; a.R = R;
+    a.doT = dDo.d; a.n_doT = n_doT; a.jitter = jitter; a.spp = spp; a.seed = seed; a.chain0 = chain_offset;
+    a.var_as_std = var_as_std;
+    GP_TRY(dInfo.outbuf(loc, info, tasks));
+    a.info = dInfo.d;
+    int rc;
+    if (!sate) {
+        GP_TRY(d1.outbuf(loc, o1, tasks * n));
+        GP_TRY(d2.outbuf(loc, o2, tasks * n * n));
+        GP_TRY(d3.outbuf(loc, o3, tasks * spp * n));
+        a.mean_out = d1.d; a.cov_out = d2.d; a.ite_out = d3.d;
+        rc = launch_ite(ctx, a);
+    } else {
+        GP_TRY(d1.outbuf(loc, o1, tasks));
+        GP_TRY(d2.outbuf(loc, o2, tasks));
+        GP_TRY(d3.outbuf(loc, o3, tasks * spp));
+        a.msate = d1.d; a.vsate = d2.d; a.sate_out = d3.d;
+        rc = launch_sate(ctx, a);
+    }
+    if (rc) return rc;
+    GP_TRY(d1.finish()); GP_TRY(d2.finish()); GP_TRY(d3.finish()); GP_TRY(dInfo.finish());
+    GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GPSLC_OK;
+}
+
+extern "C" {
+int gpslc_ite(gpslc_ctx* h, int loc, const gpslc_data* d, const double* samples, int n_outer, int n_chains, int stride,
+              const int* ret_idx, int R, const double* doT, int n_doT, double jitter, int spp, uint64_t seed, int chain_offset,
+              double* meanITE, double* covITE, double* ite, int* info) {
+    return est_common(h, loc, d, samples, n_outer, n_chains, stride, ret_idx, R, doT, n_doT, jitter, spp, seed, chain_offset, 0,
+                      false, meanITE, covITE, ite, info);
+}
+int gpslc_sate(gpslc_ctx* h, int loc, const gpslc_data* d, const double* samples, int n_outer, int n_chains, int stride,
+               const int* ret_idx, int R, const double* doT, int n_doT, double jitter, int spp, uint64_t seed, int chain_offset,
+               int var_as_std, double* meanSATE, double* varSATE, double* sate, int* info) {
+    return est_common(h, loc, d, samples, n_outer, n_chains, stride, ret_idx, R, doT, n_doT, jitter, spp, seed, chain_offset,
+                      var_as_std, true, meanSATE, varSATE, sate, info);
+}
+}

@@ -245,7 +245,9 @@ struct Pipe { uint32_t produced; uint32_t consumed; };
 template <class Gen>
 __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const int nrhs, double* scratch,
                            double* zbuf /* [MAXRHS][NCB*NB] solves, then [MAXRHS][NCB*NB] pre-solve w */,
-                           FactorSmem& sm, Pipe& pipe) {
+                           FactorSmem& sm, Pipe& pipe, const int snapJ = 1 << 30, double* snap = nullptr, const int snap_n = 0) {
+    // snapshot hook (ITE path): for panels j >= snapJ the value K - sum_{J<snapJ} L L^T (the Schur complement of the
+    // leading snapJ panels, i.e. CovITE + jitter*I) is written to snap[(c-snapJ*NB)*snap_n + (r-snapJ*NB)] (both triangles).
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int npad = NCB * NB;
@@ -261,6 +263,7 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
 #pragma unroll
             for (int ni = 0; ni < 8; ni++) { acc[ni][0] = 0.0; acc[ni][1] = 0.0; }
             double wsum[MAXRHS] = {0.0, 0.0};
+            double wsnap[MAXRHS] = {0.0, 0.0};  // residual after the leading snapJ panels only (ITE: -MeanITE)
             const int wr = tid >> 2, kq = tid & 3;  // RHS update mapping: row wr, k pair kq
             auto produce = [&](int t) {
                 const uint32_t gi = pipe.produced++;
@@ -272,7 +275,29 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                          &sm.full[st]);
             };
             if (tid == 0) for (int t = 0; t < PF && t < T; t++) produce(t);
-            for (int t = 0; t < T; t++) {
+            const bool in_tail = (j >= snapJ);
+            const bool do_snap = in_tail && (snap != nullptr);
+            const int Tsnap = in_tail ? snapJ * NSLAB : T;
+            for (int t = 0; t <= T; t++) {
+                if (in_tail && t == Tsnap) { wsnap[0] = wsum[0]; wsnap[1] = wsum[1]; }
+                if (do_snap && t == Tsnap) {
+                    // Schur complement of the leading snapJ panels for this diagonal tile (lower tiles; mirrored)
+                    const int r = j * NB + warp * 8 + g;
+#pragma unroll
+                    for (int ni = 0; ni < 8; ni++) {
+                        if (ni <= warp) {
+                            const int c = j * NB + ni * 8 + 2 * q;
+                            double v00, v01, v10, v11;
+                            gen.quad(r, r, c, v00, v01, v10, v11);
+                            const int ri = r - snapJ * NB, ci = c - snapJ * NB;
+                            if (ri < snap_n) {
+                                if (ci < snap_n) { snap[(size_t)ci * snap_n + ri] = v00 - acc[ni][0]; snap[(size_t)ri * snap_n + ci] = v00 - acc[ni][0]; }
+                                if (ci + 1 < snap_n) { snap[(size_t)(ci + 1) * snap_n + ri] = v01 - acc[ni][1]; snap[(size_t)ri * snap_n + ci + 1] = v01 - acc[ni][1]; }
+                            }
+                        }
+                    }
+                }
+                if (t == T) break;
                 if (tid == 0 && t + PF < T) produce(t + PF);
                 const uint32_t gi = pipe.consumed++;
                 const int st = gi % STAGES;
@@ -322,7 +347,14 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                 double s = wsum[rh];
                 s += __shfl_xor_sync(0xffffffffu, s, 1);
                 s += __shfl_xor_sync(0xffffffffu, s, 2);
-                if (kq == 0) sm.wvec[rh][wr] = gen.rhs(rh, j * NB + wr) - s;
+                const double yv = gen.rhs(rh, j * NB + wr);
+                if (kq == 0) sm.wvec[rh][wr] = yv - s;
+                if (in_tail) {
+                    double s2 = wsnap[rh];
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+                    if (kq == 0) zbuf[(size_t)(MAXRHS + rh) * npad + j * NB + wr] = yv - s2;
+                }
             }
             __syncthreads();
             p2_factor_diag(sm, Cs, ws, j * NB);
@@ -339,7 +371,7 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                     double s = 0.0;
                     for (int c = 0; c <= r; c++) s = fma(sm.linv[linv_off(r, c)], sm.wvec[rh][c], s);
                     zbuf[(size_t)rh * npad + j * NB + r] = s;
-                    zbuf[(size_t)(MAXRHS + rh) * npad + j * NB + r] = sm.wvec[rh][r];
+                    if (!in_tail) zbuf[(size_t)(MAXRHS + rh) * npad + j * NB + r] = sm.wvec[rh][r];
                 }
             }
             __syncthreads();
@@ -385,7 +417,28 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
             for (int mi = 0; mi < 2; mi++)
 #pragma unroll
                 for (int ni = 0; ni < 8; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
-            for (int t = 0; t < T; t++, f++) {
+            const bool do_snap = (snap != nullptr) && (j >= snapJ);
+            const int Tsnap = do_snap ? snapJ * NSLAB : T;
+            for (int t = 0; t <= T; t++, f++) {
+                if (do_snap && t == Tsnap && active) {
+                    const int r0s = (I0 + half) * NB + rw * 16 + g;
+#pragma unroll
+                    for (int ni = 0; ni < 8; ni++) {
+                        const int c = j * NB + ni * 8 + 2 * q;
+                        double v[2][2];
+                        gen.quad(r0s, r0s + 8, c, v[0][0], v[0][1], v[1][0], v[1][1]);
+                        const int ci = c - snapJ * NB;
+#pragma unroll
+                        for (int mi = 0; mi < 2; mi++) {
+                            const int ri = r0s + 8 * mi - snapJ * NB;
+                            if (ri < snap_n) {
+                                if (ci < snap_n) { const double x = v[mi][0] - acc[mi][ni][0]; snap[(size_t)ci * snap_n + ri] = x; snap[(size_t)ri * snap_n + ci] = x; }
+                                if (ci + 1 < snap_n) { const double x = v[mi][1] - acc[mi][ni][1]; snap[(size_t)(ci + 1) * snap_n + ri] = x; snap[(size_t)ri * snap_n + ci + 1] = x; }
+                            }
+                        }
+                    }
+                }
+                if (t == T) break;
                 if (tid == 0 && f + PF < F) produce(f + PF);
                 const uint32_t gi = pipe.consumed++;
                 const int st = gi % STAGES;

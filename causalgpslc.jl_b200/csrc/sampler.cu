@@ -278,6 +278,7 @@ mh_lanes_kernel(ModelDev m, ChainDev c, const int* lane_order, int outer, int j0
 }
 
 // ------------------------------------------------------------------------------------------------ ESS over U_k
+constexpr int ESS_MAX_EVALS = 200;
 // ess[c][0..4] = log u, theta, theta_min, theta_max, next scalar-stream block
 __device__ inline void ess_make_proposal(const ModelDev& m, const ChainDev& c, int chain, int k, double th, double* red) {
     const double* u = c.U + ((size_t)chain * m.nU + k) * m.n;
@@ -336,8 +337,10 @@ __global__ void __launch_bounds__(256) ess_decide_kernel(ModelDev m, ChainDev c,
         if (m.ess_rule == 0) w += -0.5 * (c.qP[chain] - c.q[(size_t)chain * m.nU + k]) / c.theta[(size_t)chain * m.n_params + 0];
         if (c.infoP[chain] != 0) w = -INFINITY;
         c.ess_evals[chain] += 1ull;
-        const bool acc = (w > e[0]);
-        s_accept = acc ? 1 : 0;
+        // Gen loops `while weight <= log(u)`: a NaN weight leaves the loop; ESS_MAX_EVALS is a safety cap (oracle has the same)
+        const bool acc = !(w <= e[0]) || (e[4] >= (double)ESS_MAX_EVALS);
+        // capped on a non-PD proposal: keep the current state (s_accept = 2: stop slicing, copy nothing)
+        s_accept = acc ? ((c.infoP[chain] != 0) ? 2 : 1) : 0;
         if (!acc) {
             double th = e[1];
             if (th < 0.0) e[2] = th; else e[3] = th;
@@ -352,6 +355,7 @@ __global__ void __launch_bounds__(256) ess_decide_kernel(ModelDev m, ChainDev c,
         }
     }
     __syncthreads();
+    if (s_accept == 2) return;
     if (s_accept) {
         double* u = c.U + ((size_t)chain * m.nU + k) * m.n;
         const double* up = c.Uprop + (size_t)chain * m.n;

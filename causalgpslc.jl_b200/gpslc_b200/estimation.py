@@ -1,0 +1,79 @@
+"""Host mirror of /root/reference/src/estimation.jl (+ likelihood.jl): ITE / SATE distributions and samples computed by
+the CUDA library (csrc/estimation.cu) from the sampler's packed posterior samples."""
+import ctypes
+
+import numpy as np
+
+from ._lib import ptr, HOST
+from .inference import GpslcData, _bind
+
+
+def retained_indices(nBurnIn, stepSize, nOuter):
+    """``nBurnIn:stepSize:nOuter`` (1-based, includes nBurnIn; src/estimation.jl:72,78) as 0-based indices."""
+    return np.arange(nBurnIn, nOuter + 1, stepSize, dtype=np.int32) - 1
+
+
+def _bind_est(lib):
+    if getattr(lib, "_est_bound", False):
+        return
+    vp, i, dbl, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_uint64
+    P = ctypes.POINTER
+    lib.gpslc_ite.restype = i
+    lib.gpslc_ite.argtypes = [vp, i, P(GpslcData), vp, i, i, i, vp, i, vp, i, dbl, i, u64, i, vp, vp, vp, vp]
+    lib.gpslc_sate.restype = i
+    lib.gpslc_sate.argtypes = [vp, i, P(GpslcData), vp, i, i, i, vp, i, vp, i, dbl, i, u64, i, i, vp, vp, vp, vp]
+    lib._est_bound = True
+
+
+def _data_struct(X, T, Y, nU):
+    keep = {"T": np.ascontiguousarray(np.asarray(T), dtype=np.float64), "Y": np.ascontiguousarray(Y, dtype=np.float64)}
+    d = GpslcData()
+    d.n = keep["T"].shape[0]
+    d.nU = int(nU or 0)
+    d.binary = int(np.asarray(T).dtype == np.bool_)
+    if X is not None:
+        keep["X"] = np.asfortranarray(np.asarray(X, dtype=np.float64))
+        d.nX = keep["X"].shape[1]
+        d.X = keep["X"].ctypes.data
+    d.T = keep["T"].ctypes.data
+    d.Y = keep["Y"].ctypes.data
+    return d, keep
+
+
+def ite(samples, X, T, Y, nU, doT, ret_idx, jitter, spp, seed=0, chain_offset=0, want_cov=False, want_samples=True, ctx=None):
+    """samples [n_outer, n_chains, stride]; doT scalar or array. Returns dict(mean [D,C,R,n], cov [D,C,R,n,n] or None,
+    samples [D,C,R*spp,n] or None, info [D,C,R])."""
+    from .kernel import default_context
+    ctx = ctx or default_context()
+    _bind(ctx.lib); _bind_est(ctx.lib)
+    samples = np.ascontiguousarray(samples, dtype=np.float64)
+    n_outer, C, stride = samples.shape
+    d, keep = _data_struct(X, T, Y, nU)
+    doT = np.ascontiguousarray(np.atleast_1d(np.asarray(doT, dtype=np.float64)))
+    ret = np.ascontiguousarray(ret_idx, dtype=np.int32)
+    D, R, n = doT.shape[0], ret.shape[0], d.n
+    mean = np.empty((D, C, R, n))
+    cov = np.empty((D, C, R, n, n)) if want_cov else None
+    smp = np.empty((D, C, R * spp, n)) if (want_samples and spp > 0) else None
+    info = np.empty((D, C, R), dtype=np.int32)
+    ctx.check(ctx.lib.gpslc_ite(ctx.h, HOST, ctypes.byref(d), ptr(samples), n_outer, C, stride, ptr(ret), R, ptr(doT), D,
+                                float(jitter), int(spp), int(seed), int(chain_offset), ptr(mean), ptr(cov), ptr(smp), ptr(info)))
+    return {"mean": mean, "cov": cov, "samples": smp, "info": info}
+
+
+def sate(samples, X, T, Y, nU, doT, ret_idx, jitter, spp, seed=0, chain_offset=0, var_as_std=True, ctx=None):
+    """Returns dict(mean [D,C,R], var [D,C,R], samples [D,C,R*spp], info)."""
+    from .kernel import default_context
+    ctx = ctx or default_context()
+    _bind(ctx.lib); _bind_est(ctx.lib)
+    samples = np.ascontiguousarray(samples, dtype=np.float64)
+    n_outer, C, stride = samples.shape
+    d, keep = _data_struct(X, T, Y, nU)
+    doT = np.ascontiguousarray(np.atleast_1d(np.asarray(doT, dtype=np.float64)))
+    ret = np.ascontiguousarray(ret_idx, dtype=np.int32)
+    D, R = doT.shape[0], ret.shape[0]
+    mean = np.empty((D, C, R)); var = np.empty((D, C, R)); smp = np.empty((D, C, R * spp)); info = np.empty((D, C, R), dtype=np.int32)
+    ctx.check(ctx.lib.gpslc_sate(ctx.h, HOST, ctypes.byref(d), ptr(samples), n_outer, C, stride, ptr(ret), R, ptr(doT), D,
+                                 float(jitter), int(spp), int(seed), int(chain_offset), int(bool(var_as_std)), ptr(mean), ptr(var),
+                                 ptr(smp), ptr(info)))
+    return {"mean": mean, "var": var, "samples": smp, "info": info}

@@ -157,6 +157,33 @@ int gpslc_sampler_get_stats(gpslc_sampler* s, unsigned long long* accepts, unsig
 int gpslc_posterior(gpslc_ctx* ctx, const gpslc_data* data, const gpslc_prior* prior, const gpslc_opts* opts,
                     double* samples_out, unsigned long long* accepts, unsigned long long* ess_evals);
 
+/* ---- L4: posterior-predictive treatment effects -------------------------------------------------------------- */
+
+/* ITEDistributions + ITEsamples (src/estimation.jl:66-109; conditionalITE :36-50; likelihoodDistribution,
+ * src/likelihood.jl:8-174) for every (doT, chain, retained sample). `samples` is the sampler's packed buffer
+ * [n_outer][n_chains][stride]; ret_idx holds the R retained 0-based outer indices (the reference's
+ * nBurnIn:stepSize:nOuter is 1-based and includes nBurnIn, src/estimation.jl:72,78). jitter = predictionCovarianceNoise.
+ * Only data->{n,nX,nU,X,T,Y} are read (X is always the observed data, src/estimation.jl:59).
+ * Outputs (each may be NULL):
+ *   meanITE [n_doT][n_chains][R][n]
+ *   covITE  [n_doT][n_chains][R][n][n]      Symmetric(CovITE) + jitter*I   (src/estimation.jl:82)
+ *   ite     [n_doT][n_chains][R*spp][n]     column j = r*spp + s is one draw N(MeanITE_r, CovITE_r) — for one chain this
+ *                                           is the column-major n x (R*spp) matrix sampleITE returns (src/driver.jl:86-89)
+ *   info    [n_doT][n_chains][R]
+ * One Cholesky of the 2n x 2n augmented matrix per (doT, chain, sample); 8 n^3 / 3 flops. */
+int gpslc_ite(gpslc_ctx* ctx, int loc, const gpslc_data* data, const double* samples, int n_outer, int n_chains, int stride,
+              const int* ret_idx, int R, const double* doT, int n_doT, double jitter, int spp, uint64_t seed, int chain_offset,
+              double* meanITE, double* covITE, double* ite, int* info);
+
+/* SATEDistributions + SATEsamples (src/estimation.jl:116-163) without forming CovITE: one n x n Cholesky with two
+ * right-hand sides per (doT, chain, sample). var_as_std=1 reproduces the reference's `normal(mean, var)` call, which
+ * uses the variance as a standard deviation; 0 draws with sqrt(var).
+ * Outputs: meanSATE, varSATE [n_doT][n_chains][R]; sate [n_doT][n_chains][R*spp] (for one chain: what sampleSATE
+ * returns, src/driver.jl:108-111); info [n_doT][n_chains][R]. */
+int gpslc_sate(gpslc_ctx* ctx, int loc, const gpslc_data* data, const double* samples, int n_outer, int n_chains, int stride,
+               const int* ret_idx, int R, const double* doT, int n_doT, double jitter, int spp, uint64_t seed, int chain_offset,
+               int var_as_std, double* meanSATE, double* varSATE, double* sate, int* info);
+
 #ifdef __cplusplus
 }
 #endif

@@ -141,6 +141,11 @@ def generate_initial_state(data, seed, chain, observe_x=False):
 
 # ------------------------------------------------------------------------------------------------ MH / ESS
 
+# Safety cap shared with the CUDA path (csrc/sampler.cu): after this many evaluations of one slice the current proposal is
+# taken (the bracket has collapsed onto the current state long before; Gen itself has no cap).
+ESS_MAX_EVALS = 200
+
+
 def mh_site(data, st, sc, site_index, name, i, j, seed, chain, it):
     """One `mh(trace, paramProposal, (drift, addr))`. Returns accepted flag."""
     spec = data.spec
@@ -192,9 +197,10 @@ def ess_u(data, st, sc, k, seed, chain, it, stats=None, ess_rule="gen_joint_weig
             if ess_rule == "likelihood_only":
                 w -= (cache[1][k] - sc.u_lp[k])
         except np.linalg.LinAlgError:
-            w, cache = -math.inf, None
+            w, cache = -math.inf, sc.rescore(st, [], [])[1]
+            st_new = st.copy()
         evals += 1
-        if w > logu:
+        if not (w <= logu) or evals >= ESS_MAX_EVALS:   # Gen: `while weight <= log(u)` (a NaN weight leaves the loop)
             break
         if theta < 0:
             tmin = theta
@@ -243,7 +249,7 @@ def ess_logit_t(data, st, sc, L_stale, seed, chain, it, stats=None):
         w, cache = sc.rescore(st_new, [fT], [])
         w += bernoulli_logpmf(data.T, st_new.logitT) - bern_old
         evals += 1
-        if w > logu:
+        if not (w <= logu) or evals >= ESS_MAX_EVALS:
             break
         if theta < 0:
             tmin = theta

@@ -1,0 +1,299 @@
+"""Parity tests proper (run on the B200 box with -m gpu): every call goes through the C ABI of libgpslc_b200.so and is
+compared with the oracle on the same seeded inputs, with the reference's golden vectors, or through size-independent
+properties at BASELINE.json's full sizes. Tolerances: covariance elements abs <= 4 ulp * scale;
+log-densities rel <= 1e-10; MeanITE / CovITE rel <= 1e-8."""
+import os
+
+import numpy as np
+import pytest
+
+import gpslc_b200 as g
+from gpslc_b200 import estimation as ge
+from gpslc_b200.inference import ChainSampler
+from oracle import kernel as ok, model as om, inference as oi, estimation as oe, data as od
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+# ------------------------------------------------------------------------------------------------ covariance build
+def test_cov_build_reference_kats(ctx, kats):
+    k = kats["rbfKernelLog_magic"]
+    X = np.array(k["X"], dtype=float)
+    assert np.array_equal(g.rbfKernelLog(X, X, k["LS"], ctx=ctx), np.array(k["expected"], dtype=float))
+    ones = np.ones((10, 5))
+    assert np.array_equal(g.rbfKernelLog(ones, ones, 0.1, ctx=ctx), np.zeros((10, 10)))
+    assert np.array_equal(g.cov_build(np.zeros((1, 1)), np.zeros((1, 1)), [[1.0]], 2.0, None, ctx=ctx)[0], [[2.0]])
+    assert np.array_equal(g.cov_build(np.zeros((1, 1)), np.zeros((1, 1)), [[1.0]], 0.0, 1e-5, ctx=ctx)[0], [[1e-5]])
+    assert np.array_equal(g.cov_build(np.zeros((1, 1)), np.zeros((1, 1)), [[1.0]], 2.0, 1e-5, ctx=ctx)[0], [[2.0 + 1e-5]])
+
+
+@pytest.mark.parametrize("n,D,batch", [(1, 1, 1), (7, 2, 3), (63, 3, 2), (64, 1, 2), (65, 12, 2), (129, 5, 3), (150, 1, 4), (272, 7, 2)])
+def test_cov_build_vs_oracle(ctx, n, D, batch):
+    rng = np.random.default_rng(n * 31 + D)
+    F = rng.standard_normal((n, D)); ls = 0.3 + 2 * rng.random((batch, D)); sc = 0.2 + rng.random(batch); nz = 0.1 + rng.random(batch)
+    K = g.cov_build(F, F, ls, sc, nz, ctx=ctx)
+    for b in range(batch):
+        want = ok.process_cov(ok.rbf_kernel_log(F, F, ls[b]), sc[b], nz[b])
+        assert np.max(np.abs(K[b] - want)) <= 4 * np.finfo(float).eps * (sc[b] + nz[b])
+    # per-batch features and X1 != X2 (src/likelihood.jl:27: K(T, doT))
+    F1 = rng.standard_normal((batch, n, D)); F2 = rng.standard_normal((batch, n, D))
+    K = g.cov_build(F1, F2, ls, sc, None, ctx=ctx)
+    for b in range(batch):
+        want = ok.process_cov(ok.rbf_kernel_log(F1[b], F2[b], ls[b]), sc[b])
+        assert np.max(np.abs(K[b] - want)) <= 4 * np.finfo(float).eps * sc[b]
+
+
+def test_cov_build_bool_features(ctx):
+    t = np.array([True, False, True, True, False])
+    K = g.cov_build(t.astype(float)[:, None], t.astype(float)[:, None], [[0.7]], 1.0, None, ctx=ctx)[0]
+    assert np.allclose(K, ok.process_cov(ok.rbf_kernel_log(t, t, 0.7), 1.0), rtol=0, atol=4e-16)
+
+
+# ------------------------------------------------------------------------------------------------ Cholesky log-density
+@pytest.mark.parametrize("n", [1, 2, 8, 63, 64, 65, 127, 128, 150, 200, 256, 272, 513])
+def test_chol_logpdf_vs_oracle(ctx, n):
+    rng = np.random.default_rng(n)
+    batch = 3
+    F = rng.standard_normal((n, 4)); ls = 0.5 + 2 * rng.random((batch, 4)); sc = 0.5 + rng.random(batch); nz = 0.05 + rng.random(batch)
+    y = rng.standard_normal((batch, n))
+    Ks = np.stack([ok.process_cov(ok.rbf_kernel_log(F, F, ls[b]), sc[b], nz[b]) for b in range(batch)])
+    want = np.array([om.mvn_logpdf_chol(y[b], Ks[b]) for b in range(batch)])
+    lp, ld, q, info = g.chol_logpdf(Ks, y, ctx=ctx)
+    assert np.all(info == 0)
+    assert np.max(np.abs(lp - want) / np.abs(want)) <= 1e-10
+    sign, ldo = np.linalg.slogdet(Ks)
+    assert np.max(np.abs(ld - ldo) / (1 + np.abs(ldo))) <= 1e-11
+    lp2, ld2, q2, info2 = g.rbf_logpdf(F, ls, sc, nz, y, ctx=ctx)      # fused build + factor
+    assert np.all(info2 == 0) and np.max(np.abs(lp2 - want) / np.abs(want)) <= 1e-10
+    lp3, *_ = g.chol_logpdf(Ks, y[0], ctx=ctx)                          # shared y
+    assert abs(lp3[0] - want[0]) <= 1e-10 * abs(want[0])
+
+
+def test_chol_not_positive_definite_reports_lapack_info(ctx):
+    K = np.eye(70); K[40, 40] = -1.0
+    lp, ld, q, info = g.chol_logpdf(K[None], np.ones(70), ctx=ctx)
+    assert info[0] == 41 and lp[0] == -np.inf                            # leading minor 41 (PosDefException(41) in Julia)
+    K = np.ones((5, 5))                                                  # singular
+    assert g.chol_logpdf(K[None], np.ones(5), ctx=ctx)[3][0] == 2
+    Ks = np.stack([np.eye(9), -np.eye(9), 2 * np.eye(9)])                # failure of one batch element does not leak
+    lp, ld, q, info = g.chol_logpdf(Ks, np.ones(9), ctx=ctx)
+    assert list(info) == [0, 1, 0] and np.isclose(ld[2], 9 * np.log(2.0)) and np.isclose(q[0], 9.0)
+
+
+def test_full_size_properties_n1024(ctx):
+    """BASELINE c3 size: closed-form checks that need no oracle factorisation."""
+    n, batch = 1024, 5
+    rng = np.random.default_rng(5)
+    y = rng.standard_normal(n)
+    # (i) huge lengthscale => K = s*11' + z*I : det and quadratic form in closed form
+    F = rng.standard_normal((n, 3)); sc = np.array([0.7, 1.3, 2.0, 0.4, 1.0]); nz = np.array([0.3, 0.5, 1.0, 2.0, 0.1])
+    lp, ld, q, info = g.rbf_logpdf(F, np.full((batch, 3), 1e9), sc, nz, y, ctx=ctx)
+    for b in range(batch):
+        ld_want = (n - 1) * np.log(nz[b]) + np.log(nz[b] + n * sc[b])
+        q_want = (y @ y) / nz[b] - sc[b] * y.sum() ** 2 / (nz[b] * (nz[b] + n * sc[b]))
+        assert abs(ld[b] - ld_want) <= 1e-9 * abs(ld_want) and abs(q[b] - q_want) <= 1e-9 * abs(q_want)
+    # (ii) fused path == dense path on the same matrices, typical hyperparameters
+    ls = 0.8 + 2 * rng.random((batch, 3))
+    K = g.cov_build(F, F, ls, sc, nz, ctx=ctx)
+    a = g.chol_logpdf(K, y, ctx=ctx); b_ = g.rbf_logpdf(F, ls, sc, nz, y, ctx=ctx)
+    assert np.all(a[3] == 0) and np.max(np.abs(a[0] - b_[0]) / np.abs(a[0])) <= 1e-12
+    # (iii) linearity of the solve: quad(2y) = 4 quad(y)
+    c = g.rbf_logpdf(F, ls, sc, nz, 2 * y, ctx=ctx)
+    assert np.max(np.abs(c[2] - 4 * b_[2]) / b_[2]) <= 1e-12 and np.allclose(c[1], b_[1], rtol=1e-14)
+
+
+# ------------------------------------------------------------------------------------------------ sampler vs oracle chain
+def _run_pair(md, X, T, Y, counts, nOuter, nMH, nES, seed, C, **opts):
+    s = ChainSampler(md.prior, X, T, Y, md.spec.nU, counts, nOuter, nMH, nES, n_chains=C, seed=seed, **opts)
+    st0 = s.state(); lp0, q0 = s.terms()
+    s.run(nOuter)
+    got = s.samples(); acc, ev = s.stats()
+    s.close()
+    return st0, lp0, q0, got, acc, ev
+
+
+@pytest.mark.parametrize("n,n_obj,nX,nU,with_u", [(48, 4, 3, 1, True), (100, 5, 2, 2, True), (150, 6, 0, 1, True),
+                                                  (64, 4, 3, 1, False), (72, 4, 0, 1, False), (130, 2, 6, 1, True)])
+def test_sampler_reproduces_oracle_chain(ctx, n, n_obj, nX, nU, with_u):
+    """Same Philox streams => the CUDA chains and the oracle chain coincide (full, no-X, no-U, neither; nU=2 exercises the
+    reference toMatrix interleave, App. B1). Accept decisions and slice-evaluation counts must be identical."""
+    counts, X, T, Y = od.synthetic(n, n_obj, max(nX, 1), seed=5)
+    if nX == 0:
+        X = None
+    md = od.model_data_from_arrays(counts if with_u else None, X, T, Y, nU=nU)
+    C, nOuter, nMH, nES, seed = 3, 3, 2, 2, 17
+    st0, lp0, q0, got, acc, ev = _run_pair(md, X, T, Y, counts if with_u else None, nOuter, nMH, nES, seed, C)
+    for c in range(C):
+        st = oi.generate_initial_state(md, seed, c)
+        packed = oi.pack_sample(md.spec, st)
+        assert np.allclose(np.nan_to_num(packed), np.nan_to_num(st0[c]), rtol=1e-12, atol=0)
+        for f in range(md.spec.nX + 2):
+            if om.factor_exists(md.spec, f):
+                want = om.factor_logpdf(md, st, f)
+                assert abs(lp0[c, f] - want) <= 1e-10 * abs(want)
+        for k in range(md.spec.nU):
+            qw, _ = om.u_prior_quad_logdet(st.U[k], counts, md.eps, md.cov)
+            assert abs(q0[c, k] - qw) <= 1e-6 * abs(qw)        # limited by the 1e-13-scale deviations inside an object
+        stats = {}
+        want, _ = oi.posterior(md, nOuter, nMH, nES, seed=seed, chain=c, stats=stats)
+        assert np.array_equal(stats["accepts"], acc[c].astype(np.int64))
+        assert stats.get("ess_evals", 0) == int(ev[c])
+        assert np.allclose(np.nan_to_num(want), np.nan_to_num(got[:, c, :]), rtol=1e-9, atol=1e-12)
+
+
+def test_sampler_option_switches(ctx):
+    counts, X, T, Y = od.synthetic(60, 3, 2, seed=2)
+    # column-wise U layout instead of the reference interleave; textbook ESS rule
+    md = od.model_data_from_arrays(counts, X, T, Y, nU=2, u_layout_reference=False)
+    *_, got, acc, ev = _run_pair(md, X, T, Y, counts, 2, 2, 2, 4, 2, u_layout_mode=1, ess_rule=1)
+    for c in range(2):
+        want, _ = oi.posterior(md, 2, 2, 2, seed=4, chain=c, ess_rule="likelihood_only")
+        assert np.allclose(want, got[:, c, :], rtol=1e-9, atol=1e-12)
+    # no-U model conditioned on the observed X (observe_x=1) vs the reference-faithful random X (App. B3)
+    md = od.model_data_from_arrays(None, X, T, Y, nU=1)
+    *_, got, acc, ev = _run_pair(md, X, T, Y, None, 2, 2, 2, 4, 2, observe_x=1)
+    for c in range(2):
+        want, _ = oi.posterior(md, 2, 2, 2, seed=4, chain=c, observe_x=True)
+        assert want.shape[1] == got.shape[2] and np.allclose(np.nan_to_num(want), np.nan_to_num(got[:, c, :]), rtol=1e-9, atol=1e-12)
+
+
+def test_chain_sharding_is_invariant(ctx):
+    """Chains 2,3 of a 4-chain run == a 2-chain run with chain_offset=2 (multi-GPU sharding)."""
+    counts, X, T, Y = od.synthetic(80, 4, 2, seed=3)
+    pri = g.getPriorParameters()
+    a = g.Posterior({**pri, "_obj_counts": counts}, X, T, Y, 1, 2, 2, 2, n_chains=4, seed=9, ctx=ctx)
+    b = g.Posterior({**pri, "_obj_counts": counts}, X, T, Y, 1, 2, 2, 2, n_chains=2, seed=9, chain_offset=2, ctx=ctx)
+    assert np.array_equal(a[:, 2:], b)
+
+
+def test_incremental_caches_stay_consistent_at_c3_shape(ctx):
+    """n=1024, nX=10: after MH sweeps + an ESS pass, the cached factor log-densities equal a from-scratch re-evaluation
+    of the final state (the invariant that lets a site re-score one factor instead of the reference's thirteen)."""
+    counts, X, T, Y = od.synthetic(1024, 16, 10)
+    s = ChainSampler(g.getPriorParameters(), X, T, Y, 1, counts, 1, 1, 1, n_chains=4, seed=1234, ctx=ctx)
+    s.mh_sweeps(1)
+    s.ess_pass(0)
+    lp, q = s.terms()
+    st = s.state()
+    s.set_state(st)
+    lp2, q2 = s.terms()
+    acc, ev = s.stats()
+    s.close()
+    assert np.max(np.abs(lp - lp2) / np.abs(lp2)) <= 1e-12 and np.allclose(q, q2, rtol=1e-12)
+    assert acc.sum() > 0 and np.all(ev >= 1)
+    # spot-check one factor of one chain against the oracle at full size (Y factor: 12-dim kernel)
+    md = od.model_data_from_arrays(counts, X, T, Y, nU=1)
+    state = om.State(st[0, :md.spec.n_params].copy(), st[0, md.spec.n_params:].reshape(1, 1024).copy())
+    want = om.factor_logpdf(md, state, 11)
+    assert abs(lp[0, 11] - want) <= 1e-10 * abs(want)
+
+
+def test_error_behaviour(ctx):
+    counts, X, T, Y = od.synthetic(20, 2, 1, seed=1)
+    pri = g.getPriorParameters()
+    with pytest.raises(g.GpslcError):                     # object counts must sum to n
+        ChainSampler(pri, X, T, Y, 1, [5, 5], 1, 1, 1, ctx=ctx)
+    with pytest.raises(g.GpslcError):                     # SigmaU needs cov < 1 + eps
+        ChainSampler({**pri, "sigmaUCov": 2.0}, X, T, Y, 1, counts, 1, 1, 1, ctx=ctx)
+    Yb = Y.copy(); Yb[3] = np.nan                         # NaN data => initial covariance check fails like PosDefException
+    with pytest.raises(g.GpslcError):
+        ChainSampler(pri, X, T, Yb * np.inf, 1, counts, 1, 1, 1, ctx=ctx).run(1)
+
+
+# ------------------------------------------------------------------------------------------------ ITE / SATE
+@pytest.mark.parametrize("n,n_obj,nX,nU,with_u", [(40, 4, 3, 1, True), (100, 5, 2, 2, True), (150, 6, 0, 1, True),
+                                                  (64, 4, 3, 1, False), (70, 5, 0, 1, False), (300, 6, 4, 1, True)])
+def test_ite_sate_vs_reference_algebra(ctx, n, n_obj, nX, nU, with_u):
+    """One augmented Cholesky (CUDA) vs the oracle's line-by-line restatement of likelihood.jl / estimation.jl
+    (LU, LU, Bunch-Kaufman + per-draw Cholesky)."""
+    counts, X, T, Y = od.synthetic(n, n_obj, max(nX, 1), seed=8)
+    if nX == 0:
+        X = None
+    md = od.model_data_from_arrays(counts if with_u else None, X, T, Y, nU=nU)
+    smp = np.stack([oi.posterior(md, 4, 1, 1, seed=5, chain=c, observe_x=True)[0] for c in range(2)], axis=1)
+    ret = np.array([1, 3], dtype=np.int32)
+    jit, spp, doTs = 1e-10, 3, (0.3, -0.5)
+    out = ge.ite(smp, X, T, Y, md.spec.nU, doTs, ret, jit, spp, seed=9, want_cov=True, ctx=ctx)
+    so = ge.sate(smp, X, T, Y, md.spec.nU, doTs, ret, jit, spp, seed=9, ctx=ctx)
+    assert out["info"].max() == 0 and so["info"].max() == 0
+    for d, doT in enumerate(doTs):
+        for c in range(2):
+            M, Cv = oe.ite_distributions(md.spec, smp[:, c, :], X, T, Y, doT, 2, 2, jit)
+            assert np.max(np.abs(M - out["mean"][d, c])) <= 1e-8 * np.max(np.abs(M))
+            assert np.max(np.abs(Cv - out["cov"][d, c])) <= 1e-8 * np.max(np.abs(Cv))
+            # draws share the normal stream; CovITE + 1e-10 I is nearly singular so the factors agree only to
+            # ~eps*cond: compare on the scale of the covariance
+            S = oe.ite_samples(M, Cv, spp, seed=9, chain=c, dot_index=d)
+            assert np.max(np.abs(S.T - out["samples"][d, c])) <= 1e-4 * np.sqrt(np.max(np.abs(Cv)))
+            ms, vs = oe.sate_distributions(M, Cv)
+            assert np.allclose(ms, so["mean"][d, c], rtol=1e-8, atol=1e-12) and np.allclose(vs, so["var"][d, c], rtol=1e-8)
+            ss = oe.sate_samples(ms, vs, spp, seed=9, chain=c, dot_index=d)
+            assert np.allclose(ss, so["samples"][d, c], rtol=1e-7, atol=1e-12)
+
+
+def test_zero_effect_identity_through_c_abi(ctx, kats):
+    """doT == T => MeanITE == 0 and CovITE == jitter exactly, for U/X present or absent (test/estimation.jl:6-247)."""
+    k = kats["conditionalITE_zero_effect"]
+    jit = kats["ITEDistributions_jitter"]["predictionCovarianceNoise"]
+    for nU, X in ((1, np.array(k["X"])), (1, None), (0, np.array(k["X"])), (0, None)):
+        nX = 0 if X is None else 1
+        spec = om.ModelSpec(1, nU, nX, False)
+        rec = np.ones(spec.n_params + nU)          # every hyperparameter 1.0, U = 1.0
+        o = ge.ite(rec[None, None, :], X, np.array(k["realT"]), np.array([0.37]), nU, [k["doT_real"]],
+                   np.array([0], dtype=np.int32), jit, 5, want_cov=True, ctx=ctx)
+        assert np.all(o["mean"] == 0.0) and np.all(o["cov"] == jit)
+        assert abs(o["samples"].mean()) <= 3 * np.sqrt(jit) and o["samples"].var() <= 10 * jit
+        s = ge.sate(rec[None, None, :], X, np.array(k["realT"]), np.array([0.37]), nU, [k["doT_real"]],
+                    np.array([0], dtype=np.int32), jit, 5, ctx=ctx)
+        assert np.all(s["mean"] == 0.0) and np.allclose(s["var"], jit, rtol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------------ public API end to end
+def test_public_api_shapes_and_golden_gate(ctx, kats):
+    """gpslc(csv) -> sampleITE(g, 0.6) -> summarizeEstimates: >= 50% of the 150 individuals' mean ITE inside the
+    reference's golden 90% interval (test/driver.jl:46-52, test/test_utils.jl:3-12)."""
+    import pandas as pd
+    k = kats["NEEC_gate"]
+    gobj = g.gpslc(os.path.join(GOLD, k["data"]), seed=1234, ctx=ctx)
+    assert len(gobj.posteriorSamples) == 24 and g.getN(gobj) == 150 and g.getNU(gobj) == 1 and gobj.X is None
+    ite = g.sampleITE(gobj, k["doT"], ctx=ctx)
+    assert ite.shape == (150, 15 * 10)
+    actual = g.summarizeEstimates(ite)
+    expected = pd.read_csv(os.path.join(GOLD, k["golden"]))
+    inside = ((expected["LowerBound"] <= actual["Mean"]) & (actual["Mean"] <= expected["UpperBound"])).mean()
+    assert inside >= k["min_fraction_inside"], inside
+    sate = g.sampleSATE(gobj, k["doT"], ctx=ctx)
+    assert sate.shape == (150,) and np.all(np.isfinite(sate))
+    M, Cv = g.ITEDistributions(gobj, k["doT"], ctx=ctx)
+    assert M.shape == (15, 150) and Cv.shape == (15, 150, 150)
+    ms, vs = g.SATEDistributions(gobj, k["doT"], ctx=ctx)
+    assert np.allclose(ms, M.mean(axis=1), rtol=1e-8, atol=1e-12) and np.allclose(vs, Cv.sum(axis=(1, 2)) / 150 ** 2, rtol=1e-7)
+    uyLS, xyLS, tyLS, yNoise, yScale, U = g.extractParameters(gobj, 10)
+    assert xyLS is None and U.shape == (150, 1) and tyLS > 0
+
+
+def test_gpslc_accepts_the_four_csv_shapes(ctx):
+    """test/gpslc.jl: full / no covariates / no objects / neither, with nOuter=5, nMHInner=1, nESInner=1."""
+    for f, has_u, has_x in (("minimal.csv", True, True), ("no_cov.csv", True, False), ("no_objects.csv", False, True),
+                            ("no_objects_no_cov.csv", False, False)):
+        h = g.getHyperParameters(); h.nOuter, h.nMHInner, h.nESInner, h.nBurnIn = 5, 1, 1, 2
+        gobj = g.gpslc(os.path.join(GOLD, "data", f), hyperparams=h, ctx=ctx)
+        assert len(gobj.posteriorSamples) == 5
+        assert (gobj.hyperparams.nU is not None) == has_u and (gobj.X is not None) == has_x
+        ite = g.sampleITE(gobj, 0.5, samplesPerPosterior=2, ctx=ctx)
+        assert ite.shape == (g.getN(gobj), 4 * 2) and np.all(np.isfinite(ite))
+
+
+def test_predict_counterfactual_effects(ctx):
+    """test/prediction.jl on n=1, plus shape/consistency on a small dataset: row d of the sweep == sampleITE at doT_d."""
+    gobj = g.gpslc([1], np.ones((1, 1)), np.array([1.0]), np.array([0.42]), ctx=ctx)
+    ite, rng_ = g.predictCounterfactualEffects(gobj, 15, minDoT=0.0, maxDoT=1.0, ctx=ctx)
+    assert ite.shape == (101, 1, 15 * 15) and -1.0 <= ite.mean() <= 1.0 and len(rng_) == 101
+    counts, X, T, Y = od.synthetic(40, 4, 2, seed=6)
+    h = g.getHyperParameters(); h.nOuter, h.nBurnIn = 6, 3
+    gobj = g.gpslc(counts, X, T, Y, hyperparams=h, ctx=ctx)
+    ite, rng_ = g.predictCounterfactualEffects(gobj, 3, fidelity=4, ctx=ctx)
+    assert ite.shape == (5, 40, 4 * 3) and rng_[0] == T.min() and rng_[-1] == T.max()
+    M0 = g.ITEDistributions(gobj, rng_[2], ctx=ctx)[0]
+    assert np.all(np.isfinite(ite)) and np.abs(ite[2].mean(axis=1) - M0.mean(axis=0)).max() < 5.0
