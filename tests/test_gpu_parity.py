@@ -196,9 +196,18 @@ def test_error_behaviour(ctx):
         ChainSampler(pri, X, T, Y, 1, [5, 5], 1, 1, 1, ctx=ctx)
     with pytest.raises(g.GpslcError):                     # SigmaU needs cov < 1 + eps
         ChainSampler({**pri, "sigmaUCov": 2.0}, X, T, Y, 1, counts, 1, 1, 1, ctx=ctx)
-    Yb = Y.copy(); Yb[3] = np.nan                         # NaN data => initial covariance check fails like PosDefException
-    with pytest.raises(g.GpslcError):
-        ChainSampler(pri, X, T, Yb * np.inf, 1, counts, 1, 1, 1, ctx=ctx).run(1)
+    # duplicated individuals + vanishing noise prior => the initial covariance is singular: the reference would throw
+    # PosDefException out of `generate`; the library returns GPSLC_ERR_NOT_PD (code 3)
+    tiny = {**pri, "yNoiseScale": 1e-300, "tNoiseScale": 1e-300, "xNoiseScale": 1e-300}
+    with pytest.raises(g.GpslcError) as ei:
+        ChainSampler(tiny, np.ones((20, 1)), np.ones(20), np.ones(20), 1, [20], 1, 1, 1, ctx=ctx)
+    assert ei.value.code == 3
+    # non-finite data does not hang the slice sampler (Gen's `while weight <= log(u)` exits on a NaN weight)
+    Yb = Y.copy(); Yb[3] = np.nan
+    s = ChainSampler(pri, X, T, Yb, 1, counts, 1, 1, 1, ctx=ctx)
+    s.run(1)
+    assert s.stats()[1][0] >= 1
+    s.close()
 
 
 # ------------------------------------------------------------------------------------------------ ITE / SATE
