@@ -1,0 +1,208 @@
+# CausalGPSLCB200.jl — `ccall` glue that re-points the hot path of CausalGPSLC.jl at libgpslc_b200.so.
+#
+# NOT EXECUTED in the build image (no Julia there): kept declarative and mechanical on purpose. Every function below
+# replaces the body of the reference function named in its docstring; signatures are the reference's.
+#
+# Usage inside the reference package (see INTEGRATION.md):
+#     include("CausalGPSLCB200.jl"); using .CausalGPSLCB200
+#     CausalGPSLCB200.init!("/path/to/libgpslc_b200.so")        # once per process, binds one GPU
+module CausalGPSLCB200
+
+using Gen
+
+const LIB = Ref{String}("libgpslc_b200.so")
+const CTX = Ref{Ptr{Cvoid}}(C_NULL)
+
+struct GpslcData            # include/gpslc.h: gpslc_data
+    n::Cint; nX::Cint; nU::Cint; binary::Cint
+    X::Ptr{Cdouble}; T::Ptr{Cdouble}; Y::Ptr{Cdouble}
+    n_obj::Cint; obj_counts::Ptr{Cint}
+    sigma_u_eps::Cdouble; sigma_u_cov::Cdouble
+end
+struct GpslcPrior           # gpslc_prior
+    shape::NTuple{13,Cdouble}; scale::NTuple{13,Cdouble}; drift::Cdouble
+end
+struct GpslcOpts            # gpslc_opts
+    nOuter::Cint; nMHInner::Cint; nESInner::Cint; n_chains::Cint
+    seed::UInt64; chain_offset::Cint; u_layout_mode::Cint; ess_rule::Cint; observe_x::Cint
+end
+
+const FAMILIES = ["uNoise", "xNoise", "tNoise", "yNoise", "xScale", "tScale", "yScale", "uxLS", "utLS", "xtLS", "uyLS", "xyLS", "tyLS"]
+
+function check(rc::Cint)
+    rc == 0 && return
+    msg = unsafe_string(ccall((:gpslc_last_error, LIB[]), Cstring, (Ptr{Cvoid},), CTX[]))
+    rc == 3 && throw(LinearAlgebra.PosDefException(0))      # GPSLC_ERR_NOT_PD: what `cholesky` throws in the reference
+    error("gpslc error $rc: $msg")
+end
+
+function init!(libpath::String=LIB[]; device::Int=0)
+    LIB[] = libpath
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:gpslc_create, LIB[]), Cint, (Cint, Ref{Ptr{Cvoid}}), device, h)
+    rc == 0 || error("gpslc_create failed ($rc): no sm_100 GPU; there is no CPU fallback")
+    CTX[] = h[]
+end
+
+"object counts of a SigmaU built by generateSigmaU (src/utils.jl:17-33); anything else is rejected"
+function sigmaUcounts(SigmaU::Matrix{Float64})
+    n = size(SigmaU, 1); counts = Cint[]; i = 1
+    while i <= n
+        j = i + 1
+        while j <= n && SigmaU[i, j] != 0.0; j += 1; end
+        push!(counts, j - i); i = j
+    end
+    counts
+end
+
+prior_struct(pp) = GpslcPrior(ntuple(k -> Float64(pp[FAMILIES[k] * "Shape"]), 13),
+                              ntuple(k -> Float64(pp[FAMILIES[k] * "Scale"]), 13), Float64(pp["drift"]))
+
+"packed record (SURVEY.md App. A7) -> Gen choicemap with the reference's addresses (src/proposal.jl:8-22, src/inference.jl:9-15)"
+function to_choicemap(rec::AbstractVector{Float64}, n, nU, nX, X, T, Y, binary)
+    cm = Gen.choicemap()
+    names = (:uNoise, :tNoise, :yNoise, :tyLS, :tScale, :yScale)
+    for (k, s) in enumerate(names); isnan(rec[k]) || (cm[s] = rec[k]); end
+    for k in 1:nX
+        isnan(rec[6+k]) || (cm[:xNoise=>k=>:Noise] = rec[6+k])
+        isnan(rec[6+nX+k]) || (cm[:xScale=>k=>:Scale] = rec[6+nX+k])
+        cm[:xtLS=>k=>:LS] = rec[6+2nX+k]; cm[:xyLS=>k=>:LS] = rec[6+3nX+k]
+        cm[:X=>k=>:X] = X[:, k]
+    end
+    np = 6 + 4nX + 2nU + nU * nX
+    for i in 1:nU
+        cm[:utLS=>i=>:LS] = rec[6+4nX+i]; cm[:uyLS=>i=>:LS] = rec[6+4nX+nU+i]
+        for j in 1:nX; cm[:uxLS=>i=>j=>:LS] = rec[6+4nX+2nU+(i-1)*nX+j]; end
+        cm[:U=>i=>:U] = rec[np+(i-1)*n+1:np+i*n]
+    end
+    cm[:Y] = Y
+    if binary
+        cm[:logitT] = rec[np+nU*n+1:np+nU*n+n]
+        for r in 1:n; cm[:T=>r=>:T] = T[r]; end
+    else
+        cm[:T] = T
+    end
+    cm
+end
+
+"""
+    Posterior(priorparams, X, T, Y, nU, nOuter, nMHInner, nESInner)
+Replaces all eight methods of src/inference.jl:4-379 (called from samplePosterior, src/driver.jl:59-69).
+Returns (posteriorSamples::Vector{Any} of choicemaps, packed::Array{Float64,3}) — the reference returns the final trace as
+second value, which samplePosterior discards (src/driver.jl:62).
+"""
+function Posterior(priorparams, X, T, Y, nU, nOuter, nMHInner, nESInner; n_chains=1, seed=UInt64(0), chain_offset=0,
+                   u_layout_mode=0, ess_rule=0, observe_x=0)
+    n = length(Y); nX = X === nothing ? 0 : size(X, 2); nu = nU === nothing ? 0 : nU
+    binary = eltype(T) == Bool
+    Tf = Float64.(T); Xf = X === nothing ? Float64[] : Matrix{Float64}(X); Yf = Float64.(Y)
+    counts = nu > 0 ? sigmaUcounts(priorparams["SigmaU"]) : Cint[]
+    np = 6 + 4nX + 2nu + nu * nX
+    stride = np + nu * n + (binary ? n : 0) + ((nu == 0 && nX > 0 && observe_x == 0) ? n * nX : 0)
+    out = Array{Float64}(undef, stride, n_chains, nOuter)          # column-major == C [nOuter][n_chains][stride]
+    GC.@preserve Tf Xf Yf counts out begin
+        d = GpslcData(n, nX, nu, binary, nX > 0 ? pointer(Xf) : C_NULL, pointer(Tf), pointer(Yf), length(counts),
+                      nu > 0 ? pointer(counts) : C_NULL, priorparams["sigmaUNoise"], priorparams["sigmaUCov"])
+        o = GpslcOpts(nOuter, something(nMHInner, 0), something(nESInner, 0), n_chains, seed, chain_offset, u_layout_mode, ess_rule, observe_x)
+        check(ccall((:gpslc_posterior, LIB[]), Cint,
+                    (Ptr{Cvoid}, Ref{GpslcData}, Ref{GpslcPrior}, Ref{GpslcOpts}, Ptr{Cdouble}, Ptr{Culonglong}, Ptr{Culonglong}),
+                    CTX[], d, prior_struct(priorparams), o, out, C_NULL, C_NULL))
+    end
+    samples = Any[to_choicemap(view(out, :, 1, i), n, nu, nX, X, T, Y, binary) for i in 1:nOuter]
+    samples, out
+end
+
+retained(h) = Cint.(collect(h.nBurnIn:h.stepSize:h.nOuter) .- 1)      # 0-based; src/estimation.jl:72,78
+
+"pack g.posteriorSamples (choicemaps) back into records for the estimation calls"
+function pack(g)
+    n = length(g.Y); nX = g.X === nothing ? 0 : size(g.X, 2); nU = g.hyperparams.nU === nothing ? 0 : g.hyperparams.nU
+    np = 6 + 4nX + 2nU + nU * nX
+    out = fill(NaN, np + nU * n, 1, length(g.posteriorSamples))
+    for (i, cm) in enumerate(g.posteriorSamples)
+        out[3, 1, i] = cm[:yNoise]; out[4, 1, i] = cm[:tyLS]; out[6, 1, i] = cm[:yScale]
+        for k in 1:nX; out[6+3nX+k, 1, i] = cm[:xyLS=>k=>:LS]; end
+        for u in 1:nU
+            out[6+4nX+nU+u, 1, i] = cm[:uyLS=>u=>:LS]
+            out[np+(u-1)*n+1:np+u*n, 1, i] = cm[:U=>u=>:U]
+        end
+    end
+    out
+end
+
+function data_struct(g, Tf, Xf, Yf)
+    nX = g.X === nothing ? 0 : size(g.X, 2); nU = g.hyperparams.nU === nothing ? 0 : g.hyperparams.nU
+    GpslcData(length(Yf), nX, nU, eltype(g.T) == Bool, nX > 0 ? pointer(Xf) : C_NULL, pointer(Tf), pointer(Yf), 0, C_NULL, 0.0, 0.0)
+end
+
+"""
+    sampleITE(g, doT; samplesPerPosterior=10)   — replaces src/driver.jl:86-89 (ITEDistributions + ITEsamples,
+src/estimation.jl:66-109, likelihoodDistribution src/likelihood.jl:8-174). Returns n × (R*samplesPerPosterior).
+"""
+function sampleITE(g, doT; samplesPerPosterior::Int=10, seed=UInt64(0))
+    packed = pack(g); ret = retained(g.hyperparams); R = length(ret); n = length(g.Y)
+    Tf = Float64.(g.T); Xf = g.X === nothing ? Float64[] : Matrix{Float64}(g.X); Yf = Float64.(g.Y)
+    out = Array{Float64}(undef, n, R * samplesPerPosterior)
+    dts = Float64[doT]
+    GC.@preserve packed ret Tf Xf Yf out dts begin
+        check(ccall((:gpslc_ite, LIB[]), Cint,
+                    (Ptr{Cvoid}, Cint, Ref{GpslcData}, Ptr{Cdouble}, Cint, Cint, Cint, Ptr{Cint}, Cint, Ptr{Cdouble}, Cint, Cdouble,
+                     Cint, UInt64, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cint}),
+                    CTX[], 0, data_struct(g, Tf, Xf, Yf), packed, size(packed, 3), 1, size(packed, 1), ret, R, dts, 1,
+                    g.hyperparams.predictionCovarianceNoise, samplesPerPosterior, seed, 0, C_NULL, C_NULL, out, C_NULL))
+    end
+    out
+end
+
+"""
+    sampleSATE(g, doT; samplesPerPosterior=10)  — replaces src/driver.jl:108-111 (SATEDistributions + SATEsamples,
+src/estimation.jl:116-163). var_as_std=1 keeps the reference's `normal(mean, var)` behaviour.
+"""
+function sampleSATE(g, doT; samplesPerPosterior::Int=10, seed=UInt64(0), var_as_std::Int=1)
+    packed = pack(g); ret = retained(g.hyperparams); R = length(ret)
+    Tf = Float64.(g.T); Xf = g.X === nothing ? Float64[] : Matrix{Float64}(g.X); Yf = Float64.(g.Y)
+    out = Vector{Float64}(undef, R * samplesPerPosterior)
+    dts = Float64[doT]
+    GC.@preserve packed ret Tf Xf Yf out dts begin
+        check(ccall((:gpslc_sate, LIB[]), Cint,
+                    (Ptr{Cvoid}, Cint, Ref{GpslcData}, Ptr{Cdouble}, Cint, Cint, Cint, Ptr{Cint}, Cint, Ptr{Cdouble}, Cint, Cdouble,
+                     Cint, UInt64, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cint}),
+                    CTX[], 0, data_struct(g, Tf, Xf, Yf), packed, size(packed, 3), 1, size(packed, 1), ret, R, dts, 1,
+                    g.hyperparams.predictionCovarianceNoise, samplesPerPosterior, seed, 0, var_as_std, C_NULL, C_NULL, out, C_NULL))
+    end
+    out
+end
+
+"""
+    predictCounterfactualEffects(g, nSamplesPerMixture; fidelity=100, minDoT, maxDoT) — replaces src/prediction.jl:23-36:
+one gpslc_ite call for all doT values instead of one sampleITE per doT.
+"""
+function predictCounterfactualEffects(g, nSamplesPerMixture::Int; fidelity::Int=100, minDoT=min(g.T...), maxDoT=max(g.T...), seed=UInt64(0))
+    doTrange = minDoT:(abs(maxDoT - minDoT) / fidelity):maxDoT
+    dts = collect(Float64, doTrange); D = length(dts)
+    packed = pack(g); ret = retained(g.hyperparams); R = length(ret); n = length(g.Y)
+    Tf = Float64.(g.T); Xf = g.X === nothing ? Float64[] : Matrix{Float64}(g.X); Yf = Float64.(g.Y)
+    out = Array{Float64}(undef, n, R * nSamplesPerMixture, D)      # C layout [D][1][R*spp][n]
+    GC.@preserve packed ret Tf Xf Yf out dts begin
+        check(ccall((:gpslc_ite, LIB[]), Cint,
+                    (Ptr{Cvoid}, Cint, Ref{GpslcData}, Ptr{Cdouble}, Cint, Cint, Cint, Ptr{Cint}, Cint, Ptr{Cdouble}, Cint, Cdouble,
+                     Cint, UInt64, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cint}),
+                    CTX[], 0, data_struct(g, Tf, Xf, Yf), packed, size(packed, 3), 1, size(packed, 1), ret, R, dts, D,
+                    g.hyperparams.predictionCovarianceNoise, nSamplesPerMixture, seed, 0, C_NULL, C_NULL, out, C_NULL))
+    end
+    permutedims(out, (3, 1, 2)), doTrange                           # ite[d, n, R*spp] as the reference returns
+end
+
+"rbfKernelLog / processCov (src/kernel.jl:24-59) through gpslc_cov_build — parity layer"
+function covBuild(X1::Matrix{Float64}, X2::Matrix{Float64}, LS::Vector{Float64}, scale::Float64, noise::Union{Float64,Nothing}=nothing)
+    n, D = size(X1); K = Matrix{Float64}(undef, n, n)
+    sc = [scale]; nz = noise === nothing ? Float64[] : [noise]
+    GC.@preserve X1 X2 LS sc nz K begin
+        check(ccall((:gpslc_cov_build, LIB[]), Cint,
+                    (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                    CTX[], 0, n, 1, D, X1, X2, 1, LS, sc, noise === nothing ? C_NULL : pointer(nz), K))
+    end
+    K
+end
+
+end # module
