@@ -210,9 +210,9 @@ def run_ours(args):
     def e2e_call(seed):
         return Posterior({**pri, "_obj_counts": counts}, X, T, Y, w["nU"], 1, e2e_sweeps, 0, n_chains=C, seed=seed,
                          chain_offset=rank * C, ctx=ctx)
-    e2e_call(1)
+    e2e_reps = 0 if args.no_e2e else 2
+    out = e2e_call(1) if not args.no_e2e else np.zeros(1)
     barrier()
-    e2e_reps = 2
     te = time.perf_counter()
     for r in range(e2e_reps):
         out = e2e_call(2 + r)
@@ -222,7 +222,7 @@ def run_ours(args):
         tt = torch.tensor([te], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         te = float(tt.item())
-    e2e_value = world * C * e2e_sweeps * e2e_reps / te
+    e2e_value = world * C * e2e_sweeps * e2e_reps / te if e2e_reps else None
     h2d = (X.size + T.size + Y.size) * 8 + 4 * len(counts) + 27 * 8
     d2h = out.size * 8
 
@@ -274,6 +274,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="development: skip the e2e leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

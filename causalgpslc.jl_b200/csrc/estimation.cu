@@ -66,6 +66,7 @@ struct IteGen {
         v00 = one(r0, c); v01 = one(r0, c + 1); v10 = one(r1, c); v11 = one(r1, c + 1);
     }
     __device__ __forceinline__ double rhs(int which, int r) const { return (r < s->n) ? s->Y[r] : 0.0; }
+    GPSLC_GENERIC_STRIP
 };
 
 

@@ -265,8 +265,11 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
             double wsum[MAXRHS] = {0.0, 0.0};
             double wsnap[MAXRHS] = {0.0, 0.0};  // residual after the leading snapJ panels only (ITE: -MeanITE)
             const int wr = tid >> 2, kq = tid & 3;  // RHS update mapping: row wr, k pair kq
+            // every thread tracks the producer counter; the issuing lane rotates over the warps so that no single warp carries
+            // the whole producer overhead (all warps advance in near lockstep through the stage ring)
             auto produce = [&](int t) {
                 const uint32_t gi = pipe.produced++;
+                if (lane != 0 || warp != (int)(gi & (FWARPS - 1))) return;
                 const int st = gi % STAGES;
                 if (gi >= STAGES) mbar_wait(&sm.empty[st], ((gi / STAGES) - 1) & 1);
                 mbar_expect_tx(&sm.full[st], SLAB_D * 8);
@@ -274,7 +277,7 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                 bulk_g2s(sm.stage + st * STAGE_D + 2 * SLAB_D, scratch + block_off(j, J, NRB) + s * SLAB_D, SLAB_D * 8,
                          &sm.full[st]);
             };
-            if (tid == 0) for (int t = 0; t < PF && t < T; t++) produce(t);
+            for (int t = 0; t < PF && t < T; t++) produce(t);
             const bool in_tail = (j >= snapJ);
             const bool do_snap = in_tail && (snap != nullptr);
             const int Tsnap = in_tail ? snapJ * NSLAB : T;
@@ -298,7 +301,7 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                     }
                 }
                 if (t == T) break;
-                if (tid == 0 && t + PF < T) produce(t + PF);
+                if (t + PF < T) produce(t + PF);
                 const uint32_t gi = pipe.consumed++;
                 const int st = gi % STAGES;
                 mbar_wait(&sm.full[st], (gi / STAGES) & 1);
@@ -333,13 +336,18 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
             {
                 const int r = j * NB + warp * 8 + g;
 #pragma unroll
-                for (int ni = 0; ni < 8; ni++) {
-                    if (ni <= warp) {
-                        const int c = j * NB + ni * 8 + 2 * q;
-                        double v00, v01, v10, v11;
-                        gen.quad(r, r, c, v00, v01, v10, v11);
-                        Cs[(warp * 8 + g) * CS_LD + ni * 8 + 2 * q] = v00 - acc[ni][0];
-                        Cs[(warp * 8 + g) * CS_LD + ni * 8 + 2 * q + 1] = v01 - acc[ni][1];
+                for (int h4 = 0; h4 < 2; h4++) {
+                    if (h4 * 4 <= warp) {
+                        double v[2][4][2];
+                        gen.template strip<4, true>(r, r, j * NB + h4 * 32 + 2 * q, v);
+#pragma unroll
+                        for (int nn = 0; nn < 4; nn++) {
+                            const int ni = h4 * 4 + nn;
+                            if (ni <= warp) {
+                                Cs[(warp * 8 + g) * CS_LD + ni * 8 + 2 * q] = v[0][nn][0] - acc[ni][0];
+                                Cs[(warp * 8 + g) * CS_LD + ni * 8 + 2 * q + 1] = v[0][nn][1] - acc[ni][1];
+                            }
+                        }
                     }
                 }
             }
@@ -393,10 +401,11 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
         const int ntile = (nblk + 1) >> 1;
         const int F = ntile * T;
         auto produce = [&](int f) {
+            const uint32_t gi = pipe.produced++;
+            if (lane != 0 || warp != (int)(gi & (FWARPS - 1))) return;
             const int tile = f / T, t = f - tile * T;
             const int I0 = j + 1 + 2 * tile;
             const bool two = (I0 + 1 < NRB);
-            const uint32_t gi = pipe.produced++;
             const int st = gi % STAGES;
             if (gi >= STAGES) mbar_wait(&sm.empty[st], ((gi / STAGES) - 1) & 1);
             mbar_expect_tx(&sm.full[st], (two ? 3 : 2) * SLAB_D * 8);
@@ -406,7 +415,7 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
             if (two) bulk_g2s(dst + SLAB_D, scratch + block_off(I0 + 1, J, NRB) + s * SLAB_D, SLAB_D * 8, &sm.full[st]);
             bulk_g2s(dst + 2 * SLAB_D, scratch + block_off(j, J, NRB) + s * SLAB_D, SLAB_D * 8, &sm.full[st]);
         };
-        if (tid == 0) for (int f = 0; f < PF && f < F; f++) produce(f);
+        for (int f = 0; f < PF && f < F; f++) produce(f);
         int f = 0;
         const int half = warp >> 2, rw = warp & 3;
         for (int tile = 0; tile < ntile; tile++) {
@@ -439,7 +448,7 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                     }
                 }
                 if (t == T) break;
-                if (tid == 0 && f + PF < F) produce(f + PF);
+                if (f + PF < F) produce(f + PF);
                 const uint32_t gi = pipe.consumed++;
                 const int st = gi % STAGES;
                 mbar_wait(&sm.full[st], (gi / STAGES) & 1);
@@ -466,14 +475,17 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                 // C = K - acc
                 const int r0 = I * NB + rw * 16 + g;
 #pragma unroll
-                for (int ni = 0; ni < 8; ni++) {
-                    const int c = j * NB + ni * 8 + 2 * q;
-                    double v00, v01, v10, v11;
-                    gen.quad(r0, r0 + 8, c, v00, v01, v10, v11);
-                    acc[0][ni][0] = v00 - acc[0][ni][0];
-                    acc[0][ni][1] = v01 - acc[0][ni][1];
-                    acc[1][ni][0] = v10 - acc[1][ni][0];
-                    acc[1][ni][1] = v11 - acc[1][ni][1];
+                for (int h4 = 0; h4 < 2; h4++) {
+                    double v[2][4][2];
+                    gen.template strip<4, false>(r0, r0 + 8, j * NB + h4 * 32 + 2 * q, v);
+#pragma unroll
+                    for (int nn = 0; nn < 4; nn++) {
+                        const int ni = h4 * 4 + nn;
+                        acc[0][ni][0] = v[0][nn][0] - acc[0][ni][0];
+                        acc[0][ni][1] = v[0][nn][1] - acc[0][ni][1];
+                        acc[1][ni][0] = v[1][nn][0] - acc[1][ni][0];
+                        acc[1][ni][1] = v[1][nn][1] - acc[1][ni][1];
+                    }
                 }
                 // L_Ij = C Linv^T : out[:, ni] = sum_{kc <= 2ni+1} Afrag(kc) x Linv[ni-tile rows][kc]
                 double* dst = scratch + block_off(I, j, NRB);

@@ -57,8 +57,64 @@ struct RbfGen {
             v00 = one(r0, c); v01 = one(r0, c + 1); v10 = one(r1, c); v11 = one(r1, c + 1);
         }
     }
+    // NI column pairs (c0 + 8*ni, +1) for rows r0 and (unless ONE_ROW) r1: the accumulator layout of one warp tile.
+    // Row features are loaded once per dimension for all NI pairs; all loads go through the read-only path.
+    template <int NI, bool ONE_ROW>
+    __device__ __forceinline__ void strip(int r0, int r1, int c0, double (&v)[2][NI][2]) const {
+        const int n = s->n;
+        if (r1 < n && r0 < n && c0 + 8 * (NI - 1) + 1 < n) {
+            double a[2][NI][2];
+#pragma unroll
+            for (int ni = 0; ni < NI; ni++) { a[0][ni][0] = 0.0; a[0][ni][1] = 0.0; a[1][ni][0] = 0.0; a[1][ni][1] = 0.0; }
+            const int D = s->D;
+#pragma unroll 2
+            for (int d = 0; d < D; d++) {
+                const double* p = s->feat[d];
+                const double w = s->w[d];
+                const double z0 = __ldg(p + r0);
+                const double z1 = ONE_ROW ? z0 : __ldg(p + r1);
+#pragma unroll
+                for (int ni = 0; ni < NI; ni++) {
+                    const double c0v = __ldg(p + c0 + 8 * ni), c1v = __ldg(p + c0 + 8 * ni + 1);
+                    double t;
+                    t = z0 - c0v; a[0][ni][0] = fma(t * w, t, a[0][ni][0]);
+                    t = z0 - c1v; a[0][ni][1] = fma(t * w, t, a[0][ni][1]);
+                    if (!ONE_ROW) {
+                        t = z1 - c0v; a[1][ni][0] = fma(t * w, t, a[1][ni][0]);
+                        t = z1 - c1v; a[1][ni][1] = fma(t * w, t, a[1][ni][1]);
+                    }
+                }
+            }
+            const double sc = s->scale, nz = s->noise;
+#pragma unroll
+            for (int ni = 0; ni < NI; ni++) {
+                const int c = c0 + 8 * ni;
+                v[0][ni][0] = sc * exp(-a[0][ni][0]) + ((r0 == c) ? nz : 0.0);
+                v[0][ni][1] = sc * exp(-a[0][ni][1]) + ((r0 == c + 1) ? nz : 0.0);
+                if (!ONE_ROW) {
+                    v[1][ni][0] = sc * exp(-a[1][ni][0]) + ((r1 == c) ? nz : 0.0);
+                    v[1][ni][1] = sc * exp(-a[1][ni][1]) + ((r1 == c + 1) ? nz : 0.0);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int ni = 0; ni < NI; ni++) {
+                const int c = c0 + 8 * ni;
+                v[0][ni][0] = one(r0, c); v[0][ni][1] = one(r0, c + 1);
+                if (!ONE_ROW) { v[1][ni][0] = one(r1, c); v[1][ni][1] = one(r1, c + 1); }
+            }
+        }
+    }
     __device__ __forceinline__ double rhs(int which, int r) const { return (r < s->n) ? s->y[which][r] : 0.0; }
 };
+
+// strip() for generators that only provide quad()
+#define GPSLC_GENERIC_STRIP                                                                                         \
+    template <int NI, bool ONE_ROW>                                                                                 \
+    __device__ __forceinline__ void strip(int r0, int r1, int c0, double (&v)[2][NI][2]) const {                    \
+        _Pragma("unroll") for (int ni = 0; ni < NI; ni++)                                                           \
+            quad(r0, r1, c0 + 8 * ni, v[0][ni][0], v[0][ni][1], v[1][ni][0], v[1][ni][1]);                          \
+    }
 
 // Dense symmetric matrix read from memory (column-major, lower triangle referenced), for the standalone
 // gpslc_chol_logpdf primitive.
@@ -72,6 +128,7 @@ struct DenseGen {
         v00 = one(r0, c); v01 = one(r0, c + 1); v10 = one(r1, c); v11 = one(r1, c + 1);
     }
     __device__ __forceinline__ double rhs(int which, int r) const { return (r < n) ? y[which][r] : 0.0; }
+    GPSLC_GENERIC_STRIP
 };
 
 }  // namespace gpslc

@@ -1,5 +1,6 @@
 // Deterministic primitives of the C ABI (parity layer): covariance build, batched Cholesky log-density on dense
 // input, and the fused build+Cholesky log-density. See include/gpslc.h for the reference call sites each replaces.
+#include <cstdlib>
 #include "context.cuh"
 #include "gens.cuh"
 
@@ -8,7 +9,11 @@ namespace gpslc {
 int ensure_workspace(Ctx* ctx, int NRB, int NCB) {
     const size_t need = scratch_doubles(NRB, NCB);
     const size_t needz = (size_t)2 * MAXRHS * NCB * NB;
-    if (ctx->slots == 0) ctx->slots = 2 * ctx->num_sms;
+    if (ctx->slots == 0) {
+        const char* e = getenv("GPSLC_CTAS_PER_SM");   // development knob: resident factor CTAs per SM (default 2)
+        const int per = (e && atoi(e) > 0) ? atoi(e) : 2;
+        ctx->slots = per * ctx->num_sms;
+    }
     if (need > ctx->slot_scratch_d) {
         if (ctx->scratch) cudaFree(ctx->scratch);
         ctx->scratch = nullptr;
