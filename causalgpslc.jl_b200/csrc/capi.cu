@@ -285,11 +285,12 @@ int gpslc_sampler_get_terms(gpslc_sampler* hs, double* factor_logpdf, double* u_
     GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return GPSLC_OK;
 }
-int gpslc_sampler_get_stats(gpslc_sampler* hs, unsigned long long* accepts, unsigned long long* ess_evals) {
+int gpslc_sampler_get_stats(gpslc_sampler* hs, unsigned long long* accepts, unsigned long long* ess_evals, unsigned long long* ess_evals_logit) {
     if (!hs) return GPSLC_ERR_ARG;
     Sampler* s = hs->s; Ctx* ctx = s->ctx;
     if (accepts) GP_CUDA(ctx, cudaMemcpyAsync(accepts, s->c.accepts, (size_t)s->m.n_chains * s->m.n_sites * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     if (ess_evals) GP_CUDA(ctx, cudaMemcpyAsync(ess_evals, s->c.ess_evals, (size_t)s->m.n_chains * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ess_evals_logit) GP_CUDA(ctx, cudaMemcpyAsync(ess_evals_logit, s->c.ess_evals_logit, (size_t)s->m.n_chains * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return GPSLC_OK;
 }
@@ -301,7 +302,7 @@ int gpslc_posterior(gpslc_ctx* h, const gpslc_data* d, const gpslc_prior* p, con
     GP_TRY(gpslc_sampler_create(h, GPSLC_HOST, d, p, o, &hs));
     int rc = gpslc_sampler_run(hs, o->nOuter);
     if (!rc) rc = gpslc_sampler_get_samples(hs, GPSLC_HOST, samples_out, nullptr);
-    if (!rc) rc = gpslc_sampler_get_stats(hs, accepts, ess_evals);
+    if (!rc) rc = gpslc_sampler_get_stats(hs, accepts, ess_evals, nullptr);
     gpslc_sampler_destroy(hs);
     return rc;
 }

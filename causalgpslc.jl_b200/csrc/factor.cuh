@@ -554,4 +554,27 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
     __syncthreads();
 }
 
+// Row i of (L x_s), s < NS, for the triangular factor held in the scratch blocks (Ioff + i/64, Joff + c/64): used for draws
+// y = L z (logitT initialisation / slice proposals, ITE samples). x: [NS][ldx].
+template <int NS>
+__device__ __forceinline__ void tri_matvec_row(const double* scratch, int NRB, int Ioff, int Joff, int i, int ncols, const double* x,
+                                               int ldx, int ns, double (&accv)[NS]) {
+#pragma unroll
+    for (int s = 0; s < NS; s++) accv[s] = 0.0;
+    const int ib = i >> 6, ri = i & 63;
+    for (int jb = 0; jb <= ib; jb++) {
+        const double* blk = scratch + block_off(Ioff + ib, Joff + jb, NRB);
+        const int jmax = (jb == ib) ? ri : 63;
+        for (int jj = 0; jj <= jmax; jj++) {
+            const int col = jb * 64 + jj;
+            if (col < ncols) {
+                const double l = blk[elem_off(ri, jj)];
+#pragma unroll
+                for (int s = 0; s < NS; s++)
+                    if (s < ns) accv[s] = fma(l, x[(size_t)s * ldx + col], accv[s]);
+            }
+        }
+    }
+}
+
 }  // namespace gpslc

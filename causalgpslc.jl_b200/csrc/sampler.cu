@@ -120,6 +120,12 @@ __global__ void __launch_bounds__(256) init_chains_kernel(ModelDev m, ChainDev c
         for (int i = threadIdx.x; i < m.n; i += blockDim.x)
             u[i] = su * (sc * st.normal_at(m.n + m.obj_of[i]) + sd * st.normal_at(i));
     }
+    if (m.binary) {
+        // logitT ~ N(0, I) when T has no parents (src/model_prior.jl:194-200); with parents init_logit_kernel overwrites it by L z
+        Stream st(m.seed, gchain, (uint32_t)m.nU, stream_b(TAG_INIT_VEC, 0));
+        double* lt = c.logitT + (size_t)chain * m.n;
+        for (int i = threadIdx.x; i < m.n; i += blockDim.x) lt[i] = st.normal_at(i);
+    }
     if (m.has_xmodel) {
         for (int k = 0; k < m.nX; k++) {
             Stream st(m.seed, gchain, (uint32_t)k, stream_b(TAG_INIT_XMODEL, 0));
@@ -373,6 +379,154 @@ __global__ void __launch_bounds__(256) ess_decide_kernel(ModelDev m, ChainDev c,
     }
 }
 
+// ------------------------------------------------------------------------------------------------ binary treatment
+__device__ __forceinline__ double softplus(double x) { return fmax(x, 0.0) + log1p(exp(-fabs(x))); }
+// sum_i log Bernoulli(T_i; expit(x_i)) (src/model_prior.jl:22-24) in the overflow-safe form
+__device__ inline double block_bernoulli(const ModelDev& m, const double* f, const double* nu, double cs, double sn, double* red) {
+    double part = 0.0;
+    for (int i = threadIdx.x; i < m.n; i += blockDim.x) {
+        const double x = f[i] * cs + nu[i] * sn;
+        part += (m.T[i] > 0.5) ? -softplus(-x) : -softplus(x);
+    }
+    return block_sum(part, red);
+}
+
+// mode 0: `generate` of logitT ~ N(0, K_T) = L z with the MODEL's T covariance (src/model_likelihood.jl:25-33,46-52,63-71)
+// mode 1: once per outer iteration, factor the covariance of src/inference.jl:216-227 (per-dimension U vectors and the DATA X —
+//         not the model's effective U / X, App. B1/B3) and draw the nES slice directions nu_j = L z_j used by the logitT
+//         elliptical-slice updates of that iteration (App. B6: the covariance is NOT refreshed while U moves)
+__global__ void __launch_bounds__(FTHREADS, 2)
+logit_prior_kernel(ModelDev m, ChainDev c, int mode, int outer, double* scratch, size_t slot_scratch, double* zbuf, size_t slot_z,
+                   double* xibuf, unsigned int* counter) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FactorSmem& sm = *reinterpret_cast<FactorSmem*>(smem_raw);
+    __shared__ RbfSpec spec;
+    __shared__ unsigned int job;
+    factor_smem_init(sm);
+    Pipe pipe{0, 0};
+    const int NCB = ceil_div(m.n, NB), FT = m.nX;
+    double* my_scratch = scratch + (size_t)blockIdx.x * slot_scratch;
+    double* my_z = zbuf + (size_t)blockIdx.x * slot_z;
+    double* xi = xibuf + (size_t)blockIdx.x * 4 * m.n;
+    for (;;) {
+        if (threadIdx.x == 0) job = atomicAdd(counter, 1u);
+        __syncthreads();
+        const int chain = (int)job;
+        if (chain >= m.n_chains) break;
+        const unsigned gchain = (unsigned)(m.chain0 + chain);
+        build_spec(m, c, chain, FT, c.Ueff + (size_t)chain * m.nU * m.n, -1, 0.0, &spec);
+        __syncthreads();
+        if (mode == 1) {
+            // override the feature columns: U_k vectors as stored (column-wise) and the observed X
+            const FactorDef& fd = m.fdef[FT];
+            for (int d = threadIdx.x; d < fd.D; d += blockDim.x) {
+                const int kind = fd.src_kind[d], idx = fd.src_idx[d];
+                spec.feat[d] = (kind == SRC_U) ? c.U + ((size_t)chain * m.nU + idx) * m.n : m.X + (size_t)idx * m.n;
+            }
+            __syncthreads();
+        }
+        RbfGen gen{&spec};
+        factor_run(gen, NCB, NCB, 0, my_scratch, my_z, sm, pipe);
+        if (threadIdx.x == 0 && sm.out.info != 0) atomicMax(&c.info[chain], sm.out.info);
+        const int ndraw = (mode == 0) ? 1 : m.nES;
+        for (int s0 = 0; s0 < ndraw; s0 += 4) {
+            const int ns = min(4, ndraw - s0);
+            __syncthreads();
+            for (int e = threadIdx.x; e < ns * m.n; e += blockDim.x) {
+                const int s = e / m.n, col = e - s * m.n;
+                Stream st(m.seed, gchain, (uint32_t)m.nU,
+                          mode == 0 ? stream_b(TAG_INIT_VEC, 0) : stream_b(TAG_ESS_NU, (uint32_t)(outer * m.nES + s0 + s)));
+                xi[(size_t)s * m.n + col] = st.normal_at(col);
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < m.n; i += blockDim.x) {
+                double accv[4];
+                tri_matvec_row<4>(my_scratch, NCB, 0, 0, i, m.n, xi, m.n, ns, accv);
+                for (int s = 0; s < ns; s++) {
+                    if (mode == 0) c.logitT[(size_t)chain * m.n + i] = accv[s];
+                    else c.nuL[((size_t)chain * m.nES + s0 + s) * m.n + i] = accv[s];
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// `elliptical_slice(trace, :logitT, zeros(n), logitTCov)` (src/inference.jl:233,293,347) for every chain: K_T is fixed during
+// the slice, so ONE factorisation with right-hand sides (f, nu) gives the quadratic form on the whole ellipse,
+// f'K^-1 f cos^2 + 2 f'K^-1 nu sin cos + nu'K^-1 nu sin^2; each shrink step then costs only the O(n) Bernoulli terms.
+__global__ void __launch_bounds__(FTHREADS, 2)
+ess_logit_kernel(ModelDev m, ChainDev c, int jj, uint32_t it, double* scratch, size_t slot_scratch, double* zbuf, size_t slot_z,
+                 unsigned int* counter) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FactorSmem& sm = *reinterpret_cast<FactorSmem*>(smem_raw);
+    __shared__ RbfSpec spec;
+    __shared__ unsigned int job;
+    __shared__ double red[32];
+    __shared__ double s_cs, s_sn;
+    __shared__ int s_done;
+    factor_smem_init(sm);
+    Pipe pipe{0, 0};
+    const int NCB = ceil_div(m.n, NB), FT = m.nX;
+    double* my_scratch = scratch + (size_t)blockIdx.x * slot_scratch;
+    double* my_z = zbuf + (size_t)blockIdx.x * slot_z;
+    for (;;) {
+        if (threadIdx.x == 0) job = atomicAdd(counter, 1u);
+        __syncthreads();
+        const int chain = (int)job;
+        if (chain >= m.n_chains) break;
+        const unsigned gchain = (unsigned)(m.chain0 + chain);
+        double* f = c.logitT + (size_t)chain * m.n;
+        const double* nu = c.nuL + ((size_t)chain * m.nES + jj) * m.n;
+        build_spec(m, c, chain, FT, c.Ueff + (size_t)chain * m.nU * m.n, -1, 0.0, &spec);
+        __syncthreads();
+        if (threadIdx.x == 0) spec.y[1] = nu;
+        __syncthreads();
+        RbfGen gen{&spec};
+        factor_run(gen, NCB, NCB, 2, my_scratch, my_z, sm, pipe);
+        const FactorOut o = sm.out;
+        const double bern0 = block_bernoulli(m, f, nu, 1.0, 0.0, red);
+        double logu = 0.0, th = 0.0, tmin = 0.0, tmax = 0.0;
+        Stream ss(m.seed, gchain, (uint32_t)m.nU, stream_b(TAG_ESS_SCALAR, it));
+        if (threadIdx.x == 0) {
+            double u, v;
+            ss.uniform_pair(u, v);
+            logu = log(u); th = 2.0 * 3.14159265358979323846 * v; tmin = th - 2.0 * 3.14159265358979323846; tmax = th;
+            s_cs = cos(th); s_sn = sin(th); s_done = (o.info != 0) ? 2 : 0;
+        }
+        __syncthreads();
+        int evals = 0;
+        double quad = o.gram[0];
+        while (s_done == 0) {
+            const double cs = s_cs, sn = s_sn;
+            const double bern = block_bernoulli(m, f, nu, cs, sn, red);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                evals++;
+                quad = cs * cs * o.gram[0] + 2.0 * sn * cs * o.gram[1] + sn * sn * o.gram[2];
+                const double w = -0.5 * (quad - o.gram[0]) + (bern - bern0);
+                if (!(w <= logu) || evals >= ESS_MAX_EVALS) {
+                    s_done = 1;
+                } else {
+                    if (th < 0.0) tmin = th; else tmax = th;
+                    th = tmin + (tmax - tmin) * ss.uniform();
+                    s_cs = cos(th); s_sn = sin(th);
+                }
+            }
+            __syncthreads();
+        }
+        if (s_done == 1) {
+            const double cs = s_cs, sn = s_sn;
+            for (int i = threadIdx.x; i < m.n; i += blockDim.x) f[i] = f[i] * cs + nu[i] * sn;
+            if (threadIdx.x == 0) {
+                c.lp[(size_t)chain * m.nF + FT] = -0.5 * (m.n * LOG_2PI + o.logdet + quad);
+                c.ess_evals_logit[chain] += (unsigned long long)evals;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ sample record
 __global__ void record_kernel(ModelDev m, ChainDev c, double* samples, int slot) {
     const int chain = blockIdx.x;
@@ -445,7 +599,6 @@ int sampler_create(Ctx* ctx, int loc, int n, int nX, int nU, int binary, const d
     *out = nullptr;
     if (n <= 0 || nX < 0 || nU < 0 || n_chains <= 0 || !T || !Y || (nX > 0 && !X)) return ctx->fail(GPSLC_ERR_ARG, "sampler_create: bad argument");
     if (nU + nX + 1 > DMAX) return ctx->fail(GPSLC_ERR_UNSUPPORTED, "sampler_create: nU + nX + 1 exceeds DMAX");
-    if (binary) return ctx->fail(GPSLC_ERR_UNSUPPORTED, "sampler_create: binary treatment is not implemented in this build");
     const bool has_u = nU > 0, has_x = nX > 0;
     if (has_u) {
         if (n_obj <= 0 || !obj_counts) return ctx->fail(GPSLC_ERR_ARG, "sampler_create: nU > 0 needs the object counts of SigmaU");
@@ -599,10 +752,13 @@ int sampler_create(Ctx* ctx, int loc, int n, int nX, int nU, int binary, const d
     S_TRY(dev_alloc(s, &c.n_active, 2));
     S_TRY(dev_alloc(s, &c.accepts, C * m.n_sites));
     S_TRY(dev_alloc(s, &c.ess_evals, C));
+    S_TRY(dev_alloc(s, &c.ess_evals_logit, C));
+    S_TRY(dev_alloc(s, &c.nuL, binary ? C * (size_t)(nES > 0 ? nES : 1) * n : 1));
     cudaMemsetAsync(c.lp, 0, C * m.nF * sizeof(double), ctx->stream);
     cudaMemsetAsync(c.lpP, 0, C * m.nF * sizeof(double), ctx->stream);
     cudaMemsetAsync(c.accepts, 0, C * m.n_sites * sizeof(unsigned long long), ctx->stream);
     cudaMemsetAsync(c.ess_evals, 0, C * sizeof(unsigned long long), ctx->stream);
+    cudaMemsetAsync(c.ess_evals_logit, 0, C * sizeof(unsigned long long), ctx->stream);
     cudaMemsetAsync(c.info, 0, C * sizeof(int), ctx->stream);
     cudaMemsetAsync(c.infoP, 0, C * sizeof(int), ctx->stream);
     const int NCB = ceil_div(n, NB);
@@ -627,6 +783,31 @@ static int launch_eval(Sampler* s, const int* list, const unsigned int* n_list_d
     return GPSLC_OK;
 }
 
+static int launch_logit_prior(Sampler* s, int mode, int outer) {
+    Ctx* ctx = s->ctx;
+    GP_CUDA(ctx, cudaFuncSetAttribute(logit_prior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
+    GP_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, sizeof(unsigned int), ctx->stream));
+    const int grid = s->m.n_chains < ctx->slots ? s->m.n_chains : ctx->slots;
+    if (!s->xibuf) { GP_CUDA(ctx, cudaMalloc(&s->xibuf, (size_t)ctx->slots * 4 * s->m.n * sizeof(double))); s->owned.push_back(s->xibuf); }
+    logit_prior_kernel<<<grid, FTHREADS, sizeof(FactorSmem), ctx->stream>>>(s->m, s->c, mode, outer, ctx->scratch, ctx->slot_scratch_d,
+                                                                          ctx->zbuf, ctx->slot_z_d, s->xibuf, ctx->counter);
+    ctx->launches++;
+    GP_CUDA(ctx, cudaGetLastError());
+    return GPSLC_OK;
+}
+
+static int launch_ess_logit(Sampler* s, int jj, uint32_t it) {
+    Ctx* ctx = s->ctx;
+    GP_CUDA(ctx, cudaFuncSetAttribute(ess_logit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
+    GP_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, sizeof(unsigned int), ctx->stream));
+    const int grid = s->m.n_chains < ctx->slots ? s->m.n_chains : ctx->slots;
+    ess_logit_kernel<<<grid, FTHREADS, sizeof(FactorSmem), ctx->stream>>>(s->m, s->c, jj, it, ctx->scratch, ctx->slot_scratch_d, ctx->zbuf,
+                                                                        ctx->slot_z_d, ctx->counter);
+    ctx->launches++;
+    GP_CUDA(ctx, cudaGetLastError());
+    return GPSLC_OK;
+}
+
 // `generate`: prior draws + initial factor log-densities. A non-PD initial factor is an error like the reference's
 // PosDefException.
 int sampler_init(Sampler* s) {
@@ -634,6 +815,7 @@ int sampler_init(Sampler* s) {
     init_chains_kernel<<<s->m.n_chains, 256, 0, ctx->stream>>>(s->m, s->c);
     ctx->launches++;
     GP_CUDA(ctx, cudaGetLastError());
+    if (s->m.binary && s->h_fdef[s->m.nX].exists) GP_TRY(launch_logit_prior(s, 0, 0));
     GP_TRY(launch_eval(s, nullptr, nullptr, s->m.n_chains, 0));
     std::vector<int> info(s->m.n_chains);
     GP_CUDA(ctx, cudaMemcpyAsync(info.data(), s->c.info, info.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -652,6 +834,8 @@ int sampler_set_state(Sampler* s, int loc, const double* packed) {
     GP_CUDA(ctx, cudaMemcpy2DAsync(s->c.theta, m.n_params * sizeof(double), packed, m.stride * sizeof(double), m.n_params * sizeof(double), m.n_chains, kind, ctx->stream));
     if (m.nU > 0)
         GP_CUDA(ctx, cudaMemcpy2DAsync(s->c.U, (size_t)m.nU * m.n * sizeof(double), packed + m.n_params, m.stride * sizeof(double), (size_t)m.nU * m.n * sizeof(double), m.n_chains, kind, ctx->stream));
+    if (m.binary)
+        GP_CUDA(ctx, cudaMemcpy2DAsync(s->c.logitT, (size_t)m.n * sizeof(double), packed + m.n_params + m.nU * m.n, m.stride * sizeof(double), (size_t)m.n * sizeof(double), m.n_chains, kind, ctx->stream));
     if (m.has_xmodel)
         GP_CUDA(ctx, cudaMemcpy2DAsync(s->c.Xmodel, (size_t)m.nX * m.n * sizeof(double), packed + m.n_params + m.nU * m.n + (m.binary ? m.n : 0), m.stride * sizeof(double), (size_t)m.nX * m.n * sizeof(double), m.n_chains, kind, ctx->stream));
     refresh_chains_kernel<<<m.n_chains, 256, 0, ctx->stream>>>(s->m, s->c);
@@ -725,9 +909,12 @@ int sampler_run(Sampler* s, int n_outer) {
         const int i = s->outer_done;
         GP_TRY(sampler_mh(s, i, s->sweeps_done, m.nMH));
         s->sweeps_done = 0;
-        if (m.nU > 0) {
-            for (int j = 0; j < m.nES; j++)
-                for (int k = 0; k < m.nU; k++) GP_TRY(sampler_ess_u(s, k, (uint32_t)(i * m.nES + j)));
+        // binary T: logitT is sliced before the U_k in every ESS pass (src/inference.jl:232-237, 292-297, 346-348)
+        const bool do_logit = m.binary && s->h_fdef[m.nX].exists;
+        if (do_logit && m.nES > 0) GP_TRY(launch_logit_prior(s, 1, i));
+        for (int j = 0; j < m.nES; j++) {
+            if (do_logit) GP_TRY(launch_ess_logit(s, j, (uint32_t)(i * m.nES + j)));
+            for (int k = 0; k < m.nU; k++) GP_TRY(sampler_ess_u(s, k, (uint32_t)(i * m.nES + j)));
         }
         record_kernel<<<m.n_chains, 256, 0, ctx->stream>>>(s->m, s->c, s->samples, i);
         ctx->launches++;

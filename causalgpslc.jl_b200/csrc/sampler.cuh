@@ -47,10 +47,11 @@ struct ModelDev {
 
 struct ChainDev {
     double *theta, *U, *Ueff, *UeffP, *Uprop, *nu, *lp, *lpP, *q, *qP, *ess, *logitT, *Xmodel;
+    double* nuL;                    // binary T: [C][nES][n] slice directions L_stale z_j drawn once per outer iteration (App. B6)
     int *info, *infoP;
     int *active_a, *active_b;       // double-buffered compacted lists of chains still slicing
     unsigned int* n_active;         // [2]
-    unsigned long long *accepts, *ess_evals;
+    unsigned long long *accepts, *ess_evals, *ess_evals_logit;
 };
 
 struct Sampler {
@@ -66,6 +67,7 @@ struct Sampler {
     int* d_lane_order = nullptr;
     int n_exist = 0;                // number of existing GP factors
     int* d_exist = nullptr;         // their ids
+    double* xibuf = nullptr;        // per-slot normal draws for L z products (binary T)
     // host copies of tables
     std::vector<FactorDef> h_fdef;
     std::vector<SiteDef> h_sites;

@@ -53,7 +53,7 @@ def _bind(lib):
     lib.gpslc_sampler_get_terms.restype = i
     lib.gpslc_sampler_get_terms.argtypes = [vp, vp, vp]
     lib.gpslc_sampler_get_stats.restype = i
-    lib.gpslc_sampler_get_stats.argtypes = [vp, vp, vp]
+    lib.gpslc_sampler_get_stats.argtypes = [vp, vp, vp, vp]
     lib.gpslc_posterior.restype = i
     lib.gpslc_posterior.argtypes = [vp, P(GpslcData), P(GpslcPrior), P(GpslcOpts), vp, vp, vp]
     lib._sampler_bound = True
@@ -182,7 +182,8 @@ class ChainSampler:
     def stats(self):
         acc = np.empty((self.n_chains, self.n_sites), dtype=np.uint64)
         ev = np.empty(self.n_chains, dtype=np.uint64)
-        self.ctx.check(self.ctx.lib.gpslc_sampler_get_stats(self.h, ptr(acc), ptr(ev)))
+        self.ess_evals_logit = np.empty(self.n_chains, dtype=np.uint64)
+        self.ctx.check(self.ctx.lib.gpslc_sampler_get_stats(self.h, ptr(acc), ptr(ev), ptr(self.ess_evals_logit)))
         return acc, ev
 
 

@@ -132,7 +132,7 @@ void gpslc_sampler_destroy(gpslc_sampler* s);
  * unused hyperparameters are NaN. n_params = length of the hyperparameter part; stride = record length. */
 int gpslc_sampler_layout(const gpslc_sampler* s, int* n_params, int* stride, int* n_sites, int* n_factors);
 /* Run n_outer more outer iterations of `Posterior` (src/inference.jl:21-57): nMHInner MH sweeps, nESInner elliptical
- * slice passes over U_1..U_nU, then record the sample. */
+ * slice passes (logitT first when T is binary, then U_1..U_nU), then record the sample. */
 int gpslc_sampler_run(gpslc_sampler* s, int n_outer);
 /* Stepping entry points used by bench.py: `count` MH sweeps of every chain (one sweep = the body of the
  * `for j = 1:nMHInner` loop, src/inference.jl:22-45) / one ESS pass over all U_k. */
@@ -148,8 +148,10 @@ int gpslc_sampler_set_state(gpslc_sampler* s, int loc, const double* packed);
  * factors that do not exist in the model variant are 0) and U_k' SigmaU^-1 U_k [n_chains][nU]. Parity layer for
  * the log-joint of src/model.jl:11-130. */
 int gpslc_sampler_get_terms(gpslc_sampler* s, double* factor_logpdf, double* u_quad);
-/* accepted MH moves per (chain, site) in sweep order, and elliptical-slice model evaluations per chain */
-int gpslc_sampler_get_stats(gpslc_sampler* s, unsigned long long* accepts, unsigned long long* ess_evals);
+/* accepted MH moves per (chain, site) in sweep order; elliptical-slice model evaluations per chain for the U_k updates and
+ * (binary T) for the logitT updates. Each pointer may be NULL. */
+int gpslc_sampler_get_stats(gpslc_sampler* s, unsigned long long* accepts, unsigned long long* ess_evals,
+                            unsigned long long* ess_evals_logit);
 
 /* One-shot form, the body of `Posterior(priorparams, X, T, Y, nU, nOuter, nMHInner, nESInner)`
  * (src/inference.jl:4-379, called from samplePosterior, src/driver.jl:59-69) for n_chains chains with host buffers:
