@@ -14,17 +14,19 @@
 // L lives in global scratch in an "atom" layout: every 8(row) x 4(k) DMMA operand fragment is 256 contiguous bytes,
 // fragments are grouped into 64(row) x 8(k) slabs of 4 KB so that one cp.async.bulk moves one pipeline operand.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace gpslc {
 
 constexpr int NB = 64;                 // panel width == row-block height
-constexpr int KB = 8;                  // k extent of one pipeline slab
+constexpr int KB = 16;                 // k extent of one pipeline slab
+constexpr int K4S = KB / 4;            // 8x4 operand atoms along k per slab
 constexpr int NSLAB = NB / KB;         // slabs per block
-constexpr int SLAB_D = NB * KB;        // doubles per slab (4 KB)
+constexpr int SLAB_D = NB * KB;        // doubles per slab (8 KB)
 constexpr int BLOCK_D = NB * NB;       // doubles per block (32 KB)
-constexpr int STAGES = 6;
-constexpr int PF = 4;                  // prefetch distance (slabs)
+constexpr int STAGES = 3;
+constexpr int PF = 2;                  // prefetch distance (slabs)
 constexpr int FWARPS = 8;
 constexpr int FTHREADS = FWARPS * 32;
 constexpr int STAGE_D = 3 * SLAB_D;    // A0 | A1 | B
@@ -94,7 +96,7 @@ __host__ __device__ inline size_t scratch_doubles(int NRB, int NCB) {
 }
 // element (r,c) inside a block: [slab c/8][r/8][k4 (c%8)/4][ (r%8)*4 + c%4 ]
 __device__ __host__ inline int elem_off(int r, int c) {
-    return (c >> 3) * SLAB_D + (r >> 3) * 64 + ((c >> 2) & 1) * 32 + (r & 7) * 4 + (c & 3);
+    return (c / KB) * SLAB_D + (r >> 3) * (K4S * 32) + ((c >> 2) % K4S) * 32 + (r & 7) * 4 + (c & 3);
 }
 __device__ __forceinline__ int linv_off(int n, int k) { return ((n >> 3) * 16 + (k >> 2)) * 32 + (n & 7) * 4 + (k & 3); }
 
@@ -273,7 +275,7 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                 const int st = gi % STAGES;
                 if (gi >= STAGES) mbar_wait(&sm.empty[st], ((gi / STAGES) - 1) & 1);
                 mbar_expect_tx(&sm.full[st], SLAB_D * 8);
-                const int J = t >> 3, s = t & 7;
+                const int J = t / NSLAB, s = t % NSLAB;
                 bulk_g2s(sm.stage + st * STAGE_D + 2 * SLAB_D, scratch + block_off(j, J, NRB) + s * SLAB_D, SLAB_D * 8,
                          &sm.full[st]);
             };
@@ -307,23 +309,23 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                 mbar_wait(&sm.full[st], (gi / STAGES) & 1);
                 const double* sB = sm.stage + st * STAGE_D + 2 * SLAB_D;
 #pragma unroll
-                for (int k4 = 0; k4 < 2; k4++) {
-                    const double a = sB[(warp * 2 + k4) * 32 + lane];
+                for (int k4 = 0; k4 < K4S; k4++) {
+                    const double a = sB[(warp * K4S + k4) * 32 + lane];
 #pragma unroll
                     for (int ni = 0; ni < 8; ni++) {
                         if (ni <= warp) {
-                            const double b = sB[(ni * 2 + k4) * 32 + lane];
+                            const double b = sB[(ni * K4S + k4) * 32 + lane];
                             dmma(acc[ni], a, b);
                         }
                     }
                 }
                 if (nrhs > 0) {
-                    // rows wr, columns (kq*2, kq*2+1) of the slab
-                    const double2 l2 = *reinterpret_cast<const double2*>(sB + (wr >> 3) * 64 + (kq >> 1) * 32 + (wr & 7) * 4 + (kq & 1) * 2);
-                    const int kcol = t * KB + kq * 2;
-                    for (int rh = 0; rh < nrhs; rh++) {
-                        const double2 z2 = *reinterpret_cast<const double2*>(zbuf + (size_t)rh * npad + kcol);
-                        wsum[rh] = fma(l2.x, z2.x, fma(l2.y, z2.y, wsum[rh]));
+                    // row wr of the diagonal block row, k columns kq, kq+4, ... of the slab (one double per 8x4 atom row)
+#pragma unroll
+                    for (int kk = 0; kk < KB / 4; kk++) {
+                        const int kc = kq + 4 * kk;    // column inside the slab
+                        const double l = sB[(wr >> 3) * (K4S * 32) + (kc >> 2) * 32 + (wr & 7) * 4 + (kc & 3)];
+                        for (int rh = 0; rh < nrhs; rh++) wsum[rh] = fma(l, zbuf[(size_t)rh * npad + t * KB + kc], wsum[rh]);
                     }
                 }
                 __syncwarp();
@@ -397,6 +399,8 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
             __syncthreads();
         }
         // =================================================================== row tiles below the diagonal
+        // Blocks j+1.. are processed two at a time (128-row tiles, warp w owns rows 16w..16w+15); an odd leftover block is
+        // processed as a 64-row tile (warp w owns rows 8w..8w+7) so that it costs half a tile of tensor time, not a full one.
         const int nblk = NRB - j - 1;
         const int ntile = (nblk + 1) >> 1;
         const int F = ntile * T;
@@ -409,7 +413,7 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
             const int st = gi % STAGES;
             if (gi >= STAGES) mbar_wait(&sm.empty[st], ((gi / STAGES) - 1) & 1);
             mbar_expect_tx(&sm.full[st], (two ? 3 : 2) * SLAB_D * 8);
-            const int J = t >> 3, s = t & 7;
+            const int J = t / NSLAB, s = t % NSLAB;
             double* dst = sm.stage + st * STAGE_D;
             bulk_g2s(dst, scratch + block_off(I0, J, NRB) + s * SLAB_D, SLAB_D * 8, &sm.full[st]);
             if (two) bulk_g2s(dst + SLAB_D, scratch + block_off(I0 + 1, J, NRB) + s * SLAB_D, SLAB_D * 8, &sm.full[st]);
@@ -417,32 +421,43 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
         };
         for (int f = 0; f < PF && f < F; f++) produce(f);
         int f = 0;
-        const int half = warp >> 2, rw = warp & 3;
-        for (int tile = 0; tile < ntile; tile++) {
-            const int I0 = j + 1 + 2 * tile;
-            const bool active = (I0 + half < NRB);
-            double acc[2][8][2];
+        const bool do_snap = (snap != nullptr) && (j >= snapJ);
+        const int Tsnap = do_snap ? snapJ * NSLAB : T;
+        // MI = 2: 128-row tile (blocks I0, I0+1); MI = 1: 64-row tile (block I0 only)
+        auto run_tile = [&](auto mi_tag, const int I0) {
+            constexpr int MI = decltype(mi_tag)::value;
+            const int half = (MI == 2) ? (warp >> 2) : 0;
+            const int I = I0 + half;                                   // block this warp works on
+            const int r8base = (MI == 2) ? (warp & 3) * 2 : warp;      // first 8-row group of this warp inside block I
+            double acc[MI][8][2];
 #pragma unroll
-            for (int mi = 0; mi < 2; mi++)
+            for (int mi = 0; mi < MI; mi++)
 #pragma unroll
                 for (int ni = 0; ni < 8; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
-            const bool do_snap = (snap != nullptr) && (j >= snapJ);
-            const int Tsnap = do_snap ? snapJ * NSLAB : T;
-            for (int t = 0; t <= T; t++, f++) {
-                if (do_snap && t == Tsnap && active) {
-                    const int r0s = (I0 + half) * NB + rw * 16 + g;
+            const int r0 = I * NB + r8base * 8 + g;
+            for (int t = 0; t <= T; t++) {
+                if (do_snap && t == Tsnap) {
 #pragma unroll
-                    for (int ni = 0; ni < 8; ni++) {
-                        const int c = j * NB + ni * 8 + 2 * q;
-                        double v[2][2];
-                        gen.quad(r0s, r0s + 8, c, v[0][0], v[0][1], v[1][0], v[1][1]);
-                        const int ci = c - snapJ * NB;
+                    for (int h4 = 0; h4 < 2; h4++) {
+                        double v[2][4][2];
+                        gen.template strip<4, MI == 1>(r0, r0 + 8, j * NB + h4 * 32 + 2 * q, v);
 #pragma unroll
-                        for (int mi = 0; mi < 2; mi++) {
-                            const int ri = r0s + 8 * mi - snapJ * NB;
-                            if (ri < snap_n) {
-                                if (ci < snap_n) { const double x = v[mi][0] - acc[mi][ni][0]; snap[(size_t)ci * snap_n + ri] = x; snap[(size_t)ri * snap_n + ci] = x; }
-                                if (ci + 1 < snap_n) { const double x = v[mi][1] - acc[mi][ni][1]; snap[(size_t)(ci + 1) * snap_n + ri] = x; snap[(size_t)ri * snap_n + ci + 1] = x; }
+                        for (int nn = 0; nn < 4; nn++) {
+                            const int ni = h4 * 4 + nn;
+                            const int ci = j * NB + ni * 8 + 2 * q - snapJ * NB;
+#pragma unroll
+                            for (int mi = 0; mi < MI; mi++) {
+                                const int ri = r0 + 8 * mi - snapJ * NB;
+                                if (ri < snap_n) {
+#pragma unroll
+                                    for (int e = 0; e < 2; e++) {
+                                        if (ci + e < snap_n) {
+                                            const double x = v[mi][nn][e] - acc[mi][ni][e];
+                                            snap[(size_t)(ci + e) * snap_n + ri] = x;
+                                            snap[(size_t)ri * snap_n + ci + e] = x;
+                                        }
+                                    }
+                                }
                             }
                         }
                     }
@@ -452,83 +467,86 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                 const uint32_t gi = pipe.consumed++;
                 const int st = gi % STAGES;
                 mbar_wait(&sm.full[st], (gi / STAGES) & 1);
-                if (active) {
-                    const double* sA = sm.stage + st * STAGE_D + half * SLAB_D + (rw * 2) * 64;
+                {
+                    const double* sA = sm.stage + st * STAGE_D + half * SLAB_D + r8base * (K4S * 32);
                     const double* sB = sm.stage + st * STAGE_D + 2 * SLAB_D;
 #pragma unroll
-                    for (int k4 = 0; k4 < 2; k4++) {
-                        const double a0 = sA[k4 * 32 + lane];
-                        const double a1 = sA[64 + k4 * 32 + lane];
+                    for (int k4 = 0; k4 < K4S; k4++) {
+                        double a[MI];
+#pragma unroll
+                        for (int mi = 0; mi < MI; mi++) a[mi] = sA[mi * (K4S * 32) + k4 * 32 + lane];
 #pragma unroll
                         for (int ni = 0; ni < 8; ni++) {
-                            const double b = sB[(ni * 2 + k4) * 32 + lane];
-                            dmma(acc[0][ni], a0, b);
-                            dmma(acc[1][ni], a1, b);
+                            const double b = sB[(ni * K4S + k4) * 32 + lane];
+#pragma unroll
+                            for (int mi = 0; mi < MI; mi++) dmma(acc[mi][ni], a[mi], b);
                         }
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.empty[st]);
+                f++;
             }
-            if (active) {
-                const int I = I0 + half;
-                // C = K - acc
-                const int r0 = I * NB + rw * 16 + g;
+            // C = K - acc
 #pragma unroll
-                for (int h4 = 0; h4 < 2; h4++) {
-                    double v[2][4][2];
-                    gen.template strip<4, false>(r0, r0 + 8, j * NB + h4 * 32 + 2 * q, v);
+            for (int h4 = 0; h4 < 2; h4++) {
+                double v[2][4][2];
+                gen.template strip<4, MI == 1>(r0, r0 + 8, j * NB + h4 * 32 + 2 * q, v);
 #pragma unroll
-                    for (int nn = 0; nn < 4; nn++) {
-                        const int ni = h4 * 4 + nn;
-                        acc[0][ni][0] = v[0][nn][0] - acc[0][ni][0];
-                        acc[0][ni][1] = v[0][nn][1] - acc[0][ni][1];
-                        acc[1][ni][0] = v[1][nn][0] - acc[1][ni][0];
-                        acc[1][ni][1] = v[1][nn][1] - acc[1][ni][1];
+                for (int nn = 0; nn < 4; nn++)
+#pragma unroll
+                    for (int mi = 0; mi < MI; mi++) {
+                        acc[mi][h4 * 4 + nn][0] = v[mi][nn][0] - acc[mi][h4 * 4 + nn][0];
+                        acc[mi][h4 * 4 + nn][1] = v[mi][nn][1] - acc[mi][h4 * 4 + nn][1];
                     }
-                }
-                // L_Ij = C Linv^T : out[:, ni] = sum_{kc <= 2ni+1} Afrag(kc) x Linv[ni-tile rows][kc]
-                double* dst = scratch + block_off(I, j, NRB);
+            }
+            // L_Ij = C Linv^T : out[:, ni] = sum_{kc <= 2ni+1} Afrag(kc) x Linv[ni-tile rows][kc]; A-fragments are rebuilt from the
+            // accumulators with quad shuffles (lane (g,q) needs C[g][4h+q], held by lane (g, 2h + q/2), element q%2)
+            double* dst = scratch + block_off(I, j, NRB);
 #pragma unroll
-                for (int nig = 0; nig < 8; nig += 4) {
-                    double o[2][4][2];
+            for (int nig = 0; nig < 8; nig += 4) {
+                double o[MI][4][2];
 #pragma unroll
-                    for (int mi = 0; mi < 2; mi++)
+                for (int mi = 0; mi < MI; mi++)
 #pragma unroll
-                        for (int nn = 0; nn < 4; nn++) { o[mi][nn][0] = 0.0; o[mi][nn][1] = 0.0; }
+                    for (int nn = 0; nn < 4; nn++) { o[mi][nn][0] = 0.0; o[mi][nn][1] = 0.0; }
 #pragma unroll
-                    for (int kc = 0; kc < 16; kc++) {
-                        if (kc <= 2 * (nig + 3) + 1) {
-                            const int tt = kc >> 1, hh = kc & 1;
-                            const int src = (lane & ~3) | (2 * hh + (q >> 1));
-                            double a[2];
+                for (int kc = 0; kc < 16; kc++) {
+                    if (kc <= 2 * (nig + 3) + 1) {
+                        const int tt = kc >> 1, hh = kc & 1;
+                        const int src = (lane & ~3) | (2 * hh + (q >> 1));
+                        double a[MI];
 #pragma unroll
-                            for (int mi = 0; mi < 2; mi++) {
-                                const double v0 = __shfl_sync(0xffffffffu, acc[mi][tt][0], src);
-                                const double v1 = __shfl_sync(0xffffffffu, acc[mi][tt][1], src);
-                                a[mi] = (q & 1) ? v1 : v0;
-                            }
-#pragma unroll
-                            for (int nn = 0; nn < 4; nn++) {
-                                const int ni = nig + nn;
-                                if (kc <= 2 * ni + 1) {
-                                    const double b = sm.linv[(ni * 16 + kc) * 32 + lane];
-                                    dmma(o[0][nn], a[0], b);
-                                    dmma(o[1][nn], a[1], b);
-                                }
-                            }
+                        for (int mi = 0; mi < MI; mi++) {
+                            const double v0 = __shfl_sync(0xffffffffu, acc[mi][tt][0], src);
+                            const double v1 = __shfl_sync(0xffffffffu, acc[mi][tt][1], src);
+                            a[mi] = (q & 1) ? v1 : v0;
                         }
-                    }
-#pragma unroll
-                    for (int mi = 0; mi < 2; mi++)
 #pragma unroll
                         for (int nn = 0; nn < 4; nn++) {
                             const int ni = nig + nn;
-                            double2 v = make_double2(o[mi][nn][0], o[mi][nn][1]);
-                            *reinterpret_cast<double2*>(dst + ni * SLAB_D + (rw * 2 + mi) * 64 + (q >> 1) * 32 + g * 4 + (q & 1) * 2) = v;
+                            if (kc <= 2 * ni + 1) {
+                                const double b = sm.linv[(ni * 16 + kc) * 32 + lane];
+#pragma unroll
+                                for (int mi = 0; mi < MI; mi++) dmma(o[mi][nn], a[mi], b);
+                            }
                         }
+                    }
                 }
+#pragma unroll
+                for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+                    for (int nn = 0; nn < 4; nn++) {
+                        const int ni = nig + nn;
+                        double2 v = make_double2(o[mi][nn][0], o[mi][nn][1]);
+                        *reinterpret_cast<double2*>(dst + elem_off((r8base + mi) * 8 + g, ni * 8 + 2 * q)) = v;
+                    }
             }
+        };
+        for (int tile = 0; tile < ntile; tile++) {
+            const int I0 = j + 1 + 2 * tile;
+            if (I0 + 1 < NRB) run_tile(std::integral_constant<int, 2>{}, I0);
+            else run_tile(std::integral_constant<int, 1>{}, I0);
         }
         fence_proxy_async();
         __syncthreads();
