@@ -32,6 +32,8 @@ constexpr int FTHREADS = FWARPS * 32;
 constexpr int STAGE_D = 3 * SLAB_D;    // A0 | A1 | B
 constexpr int MAXRHS = 2;
 constexpr int CS_LD = 65;              // P2 workspace leading dimension
+constexpr int LINV_D = 72 * 32;        // atoms (n8, k4) with k4 <= 2*n8+1, row n8 starts at atom n8*(n8+1)
+constexpr int CF_DIMS = 24;            // feature dimensions staged per panel (more dimensions fall back to global loads)
 
 struct FactorOut {
     double logdet;      // log det K
@@ -41,8 +43,11 @@ struct FactorOut {
 
 struct __align__(128) FactorSmem {
     double stage[STAGES * STAGE_D];    // 72 KB; P2 aliases it as workspace while no copy is in flight
-    double linv[BLOCK_D];              // 32 KB; inverse of the current diagonal block, atom layout [n8][k4:16][32]
+    double linv[LINV_D];               // 18 KB; inverse of the current diagonal block: the 72 8x4 atoms on/below the diagonal
+    double colfeat[CF_DIMS * NB];      // 12 KB; feature values of the current panel's 64 columns (covariance generation)
     double wvec[MAXRHS][NB];           // w_j (pre-solve) / scratch
+    double part[4][NB];                // per-row partial sums: log L_ii, z0.z0, z0.z1, z1.z1 (kept out of registers)
+    double* snap; int snapJ, snap_n;   // snapshot hook parameters
     double red[32];
     unsigned long long full[STAGES];
     unsigned long long empty[STAGES];
@@ -87,18 +92,17 @@ __device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
 }
 
 // ---------------------------------------------------------------------------------------------- scratch layout
-// blocks of panel J are contiguous: (I,J), I = J..NRB-1
-__device__ __host__ inline size_t block_off(int I, int J, int NRB) {
-    return ((size_t)J * NRB - (size_t)J * (J - 1) / 2 + (I - J)) * BLOCK_D;
-}
-__host__ __device__ inline size_t scratch_doubles(int NRB, int NCB) {
-    return ((size_t)NCB * NRB - (size_t)NCB * (NCB - 1) / 2) * BLOCK_D;
-}
+// blocks of row-block I are contiguous: (I,0), (I,1), ..., (I,I) — the k-loop of a row tile therefore streams one contiguous
+// region per operand (slab t of row I lives at row_off(I) + t*SLAB_D)
+__device__ __host__ inline size_t row_off(int I) { return ((size_t)I * (I + 1) / 2) * BLOCK_D; }
+__device__ __host__ inline size_t block_off(int I, int J, int /*NRB*/) { return row_off(I) + (size_t)J * BLOCK_D; }
+__host__ __device__ inline size_t scratch_doubles(int NRB, int /*NCB*/) { return row_off(NRB); }
 // element (r,c) inside a block: [slab c/8][r/8][k4 (c%8)/4][ (r%8)*4 + c%4 ]
 __device__ __host__ inline int elem_off(int r, int c) {
     return (c / KB) * SLAB_D + (r >> 3) * (K4S * 32) + ((c >> 2) % K4S) * 32 + (r & 7) * 4 + (c & 3);
 }
-__device__ __forceinline__ int linv_off(int n, int k) { return ((n >> 3) * 16 + (k >> 2)) * 32 + (n & 7) * 4 + (k & 3); }
+__device__ __forceinline__ int linv_off(int n, int k) { return ((n >> 3) * ((n >> 3) + 1) + (k >> 2)) * 32 + (n & 7) * 4 + (k & 3); }
+__device__ __forceinline__ bool linv_has(int n, int k) { return (k >> 2) <= 2 * (n >> 3) + 1; }
 
 __device__ inline void factor_smem_init(FactorSmem& sm) {
     if (threadIdx.x == 0) {
@@ -205,7 +209,7 @@ __device__ inline void p2_factor_diag(FactorSmem& sm, double* Cs, double* ws, in
     // ---- full inverse into sm.linv (atom layout). Diagonal 16-blocks first (with explicit zeros above the diagonal).
     for (int idx = tid; idx < 4 * 256; idx += FTHREADS) {
         const int b = idx >> 8, i = (idx >> 4) & 15, c = idx & 15;
-        sm.linv[linv_off(b * 16 + i, b * 16 + c)] = li16[(b * 16 + i) * 17 + c];
+        if (linv_has(b * 16 + i, b * 16 + c)) sm.linv[linv_off(b * 16 + i, b * 16 + c)] = li16[(b * 16 + i) * 17 + c];
     }
     __syncthreads();
     for (int d = 1; d < 4; d++) {
@@ -218,7 +222,8 @@ __device__ inline void p2_factor_diag(FactorSmem& sm, double* Cs, double* ws, in
             for (int k = j; k < i; k++) {
 #pragma unroll
                 for (int m = 0; m < 16; m++)
-                    s = fma(Cs[(16 * i + a) * CS_LD + 16 * k + m], sm.linv[linv_off(16 * k + m, 16 * j + b)], s);
+                    if (k > j || m >= b)   // X_jj is lower triangular (entries above its diagonal are not stored)
+                        s = fma(Cs[(16 * i + a) * CS_LD + 16 * k + m], sm.linv[linv_off(16 * k + m, 16 * j + b)], s);
             }
             Ts[(bi * 16 + a) * 17 + b] = s;
         }
@@ -253,12 +258,14 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int npad = NCB * NB;
-    double logdet_part = 0.0, g00 = 0.0, g01 = 0.0, g11 = 0.0;
-    if (tid == 0) sm.info = 0;
+    if (tid == 0) { sm.info = 0; sm.snap = snap; sm.snapJ = snapJ; sm.snap_n = snap_n; }
+    if (tid < NB) { sm.part[0][tid] = 0.0; sm.part[1][tid] = 0.0; sm.part[2][tid] = 0.0; sm.part[3][tid] = 0.0; }
     __syncthreads();
 
     for (int j = 0; j < NCB; j++) {
         const int T = j * NSLAB;  // slabs in the k-loop of this panel
+        gen.stage_cols(j * NB, sm.colfeat);
+        __syncthreads();
         // =================================================================== diagonal tile
         {
             double acc[8][2];
@@ -275,9 +282,7 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                 const int st = gi % STAGES;
                 if (gi >= STAGES) mbar_wait(&sm.empty[st], ((gi / STAGES) - 1) & 1);
                 mbar_expect_tx(&sm.full[st], SLAB_D * 8);
-                const int J = t / NSLAB, s = t % NSLAB;
-                bulk_g2s(sm.stage + st * STAGE_D + 2 * SLAB_D, scratch + block_off(j, J, NRB) + s * SLAB_D, SLAB_D * 8,
-                         &sm.full[st]);
+                bulk_g2s(sm.stage + st * STAGE_D + 2 * SLAB_D, scratch + row_off(j) + (size_t)t * SLAB_D, SLAB_D * 8, &sm.full[st]);
             };
             for (int t = 0; t < PF && t < T; t++) produce(t);
             const bool in_tail = (j >= snapJ);
@@ -341,7 +346,7 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                 for (int h4 = 0; h4 < 2; h4++) {
                     if (h4 * 4 <= warp) {
                         double v[2][4][2];
-                        gen.template strip<4, true>(r, r, j * NB + h4 * 32 + 2 * q, v);
+                        gen.template strip<4, true>(r, r, j * NB + h4 * 32 + 2 * q, v, sm.colfeat, h4 * 32 + 2 * q);
 #pragma unroll
                         for (int nn = 0; nn < 4; nn++) {
                             const int ni = h4 * 4 + nn;
@@ -375,7 +380,7 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                     const int r = idx >> 6, c = idx & 63;
                     dst[elem_off(r, c)] = (c <= r) ? Cs[r * CS_LD + c] : 0.0;
                 }
-                if (tid < NB) logdet_part += log(Cs[tid * CS_LD + tid]);
+                if (tid < NB) sm.part[0][tid] += log(Cs[tid * CS_LD + tid]);
                 if (tid < NB * nrhs) {
                     const int rh = tid >> 6, r = tid & 63;
                     double s = 0.0;
@@ -388,11 +393,11 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
             if (tid < NB && nrhs > 0) {
                 // gram sums: read back z from global (just written by this CTA; visible after the barrier)
                 const double z0 = zbuf[j * NB + tid];
-                g00 = fma(z0, z0, g00);
+                sm.part[1][tid] = fma(z0, z0, sm.part[1][tid]);
                 if (nrhs > 1) {
                     const double z1 = zbuf[(size_t)npad + j * NB + tid];
-                    g01 = fma(z0, z1, g01);
-                    g11 = fma(z1, z1, g11);
+                    sm.part[2][tid] = fma(z0, z1, sm.part[2][tid]);
+                    sm.part[3][tid] = fma(z1, z1, sm.part[3][tid]);
                 }
             }
             fence_proxy_async();   // generic-proxy writes (smem workspace, global L_jj) before later async-proxy copies
@@ -404,25 +409,28 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
         const int nblk = NRB - j - 1;
         const int ntile = (nblk + 1) >> 1;
         const int F = ntile * T;
-        auto produce = [&](int f) {
+        // producer position (tile, slab) advances with every call; all threads keep it in step, the elected lane issues
+        int ptile = 0, pt = 0, prem = F;
+        auto produce = [&]() {
+            prem--;
             const uint32_t gi = pipe.produced++;
+            const int tile = ptile, t = pt;
+            if (++pt == T) { pt = 0; ptile++; }
             if (lane != 0 || warp != (int)(gi & (FWARPS - 1))) return;
-            const int tile = f / T, t = f - tile * T;
             const int I0 = j + 1 + 2 * tile;
             const bool two = (I0 + 1 < NRB);
             const int st = gi % STAGES;
             if (gi >= STAGES) mbar_wait(&sm.empty[st], ((gi / STAGES) - 1) & 1);
             mbar_expect_tx(&sm.full[st], (two ? 3 : 2) * SLAB_D * 8);
-            const int J = t / NSLAB, s = t % NSLAB;
             double* dst = sm.stage + st * STAGE_D;
-            bulk_g2s(dst, scratch + block_off(I0, J, NRB) + s * SLAB_D, SLAB_D * 8, &sm.full[st]);
-            if (two) bulk_g2s(dst + SLAB_D, scratch + block_off(I0 + 1, J, NRB) + s * SLAB_D, SLAB_D * 8, &sm.full[st]);
-            bulk_g2s(dst + 2 * SLAB_D, scratch + block_off(j, J, NRB) + s * SLAB_D, SLAB_D * 8, &sm.full[st]);
+            const size_t so = (size_t)t * SLAB_D;
+            bulk_g2s(dst, scratch + row_off(I0) + so, SLAB_D * 8, &sm.full[st]);
+            if (two) bulk_g2s(dst + SLAB_D, scratch + row_off(I0 + 1) + so, SLAB_D * 8, &sm.full[st]);
+            bulk_g2s(dst + 2 * SLAB_D, scratch + row_off(j) + so, SLAB_D * 8, &sm.full[st]);
         };
-        for (int f = 0; f < PF && f < F; f++) produce(f);
-        int f = 0;
-        const bool do_snap = (snap != nullptr) && (j >= snapJ);
-        const int Tsnap = do_snap ? snapJ * NSLAB : T;
+        for (int f = 0; f < PF && f < F; f++) produce();
+        // slab index at which the Schur-complement snapshot is taken, or -1 (parameters live in shared memory)
+        const int Tsnap = (snap != nullptr && j >= snapJ) ? snapJ * NSLAB : -1;
         // MI = 2: 128-row tile (blocks I0, I0+1); MI = 1: 64-row tile (block I0 only)
         auto run_tile = [&](auto mi_tag, const int I0) {
             constexpr int MI = decltype(mi_tag)::value;
@@ -436,11 +444,13 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                 for (int ni = 0; ni < 8; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
             const int r0 = I * NB + r8base * 8 + g;
             for (int t = 0; t <= T; t++) {
-                if (do_snap && t == Tsnap) {
+                if (t == Tsnap) {
+                    double* snap = sm.snap;
+                    const int snapJ = sm.snapJ, snap_n = sm.snap_n;
 #pragma unroll
                     for (int h4 = 0; h4 < 2; h4++) {
                         double v[2][4][2];
-                        gen.template strip<4, MI == 1>(r0, r0 + 8, j * NB + h4 * 32 + 2 * q, v);
+                        gen.template strip<4, MI == 1>(r0, r0 + 8, j * NB + h4 * 32 + 2 * q, v, sm.colfeat, h4 * 32 + 2 * q);
 #pragma unroll
                         for (int nn = 0; nn < 4; nn++) {
                             const int ni = h4 * 4 + nn;
@@ -463,7 +473,7 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                     }
                 }
                 if (t == T) break;
-                if (f + PF < F) produce(f + PF);
+                if (prem > 0) produce();
                 const uint32_t gi = pipe.consumed++;
                 const int st = gi % STAGES;
                 mbar_wait(&sm.full[st], (gi / STAGES) & 1);
@@ -481,17 +491,19 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
 #pragma unroll
                             for (int mi = 0; mi < MI; mi++) dmma(acc[mi][ni], a[mi], b);
                         }
+                        // keep the scheduler from hoisting the next steps' operand loads: with 64 accumulator registers live,
+                        // deeper load hoisting spills accumulators inside this loop
+                        asm volatile("" ::: "memory");
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.empty[st]);
-                f++;
             }
             // C = K - acc
 #pragma unroll
             for (int h4 = 0; h4 < 2; h4++) {
                 double v[2][4][2];
-                gen.template strip<4, MI == 1>(r0, r0 + 8, j * NB + h4 * 32 + 2 * q, v);
+                gen.template strip<4, MI == 1>(r0, r0 + 8, j * NB + h4 * 32 + 2 * q, v, sm.colfeat, h4 * 32 + 2 * q);
 #pragma unroll
                 for (int nn = 0; nn < 4; nn++)
 #pragma unroll
@@ -526,7 +538,7 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                         for (int nn = 0; nn < 4; nn++) {
                             const int ni = nig + nn;
                             if (kc <= 2 * ni + 1) {
-                                const double b = sm.linv[(ni * 16 + kc) * 32 + lane];
+                                const double b = sm.linv[(ni * (ni + 1) + kc) * 32 + lane];
 #pragma unroll
                                 for (int mi = 0; mi < MI; mi++) dmma(o[mi][nn], a[mi], b);
                             }
@@ -551,23 +563,13 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
         fence_proxy_async();
         __syncthreads();
     }
-    // ---- block reductions
-    double vals[4] = {logdet_part, g00, g01, g11};
-#pragma unroll
-    for (int v = 0; v < 4; v++) {
-        double s = vals[v];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) sm.red[warp * 4 + v] = s;
-    }
+    // ---- reductions
     __syncthreads();
-    if (tid == 0) {
-        double s[4] = {0, 0, 0, 0};
-        for (int w = 0; w < FWARPS; w++)
-            for (int v = 0; v < 4; v++) s[v] += sm.red[w * 4 + v];
-        sm.out.logdet = 2.0 * s[0];
-        sm.out.gram[0] = s[1]; sm.out.gram[1] = s[2]; sm.out.gram[2] = s[3];
-        sm.out.info = sm.info;
+    if (tid < 4) {
+        double acc = 0.0;
+        for (int i = 0; i < NB; i++) acc += sm.part[tid][i];
+        if (tid == 0) { sm.out.logdet = 2.0 * acc; sm.out.info = sm.info; }
+        else sm.out.gram[tid - 1] = acc;
     }
     __syncthreads();
 }

@@ -5,7 +5,39 @@
 #include "common.cuh"
 #include "factor.cuh"
 
+#ifndef GPSLC_STAGE_COLS
+#define GPSLC_STAGE_COLS 1
+#endif
+
 namespace gpslc {
+
+// exp(-a) for a >= 0 without branches, so that the 16 independent evaluations of a strip interleave in the FP64 pipe instead
+// of running as 16 serial dependent chains through the library routine's special-case branches. Cody-Waite reduction
+// x = k ln2 + r, |r| <= ln2/2, degree-13 Taylor polynomial in Horner form (truncation 4e-18), result scaled through the
+// exponent field; values below 2^-1020 are flushed to zero (the library would return denormals). Max error ~1.5 ulp.
+__device__ __forceinline__ double exp_neg(double a) {
+    const double x = -a;
+    const double kd = rint(x * 1.4426950408889634074);
+    double r = fma(kd, -6.93147180369123816490e-01, x);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;
+    p = fma(p, r, 2.08767569878681e-09);
+    p = fma(p, r, 2.505210838544172e-08);
+    p = fma(p, r, 2.755731922398589e-07);
+    p = fma(p, r, 2.7557319223985893e-06);
+    p = fma(p, r, 2.48015873015873e-05);
+    p = fma(p, r, 1.984126984126984e-04);
+    p = fma(p, r, 1.388888888888889e-03);
+    p = fma(p, r, 8.333333333333333e-03);
+    p = fma(p, r, 4.1666666666666664e-02);
+    p = fma(p, r, 1.6666666666666666e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int k = (int)kd;
+    const double v = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+    return (k < -1020) ? 0.0 : v;
+}
 
 // K[r][c] = scale * exp(-sum_d w_d (f_d[r]-f_d[c])^2) + noise*[r==c],  w_d = 1/ls_d^2  (no 1/2, lengthscale squared:
 // src/kernel.jl:17). Rows/cols >= n are identity padding.
@@ -59,15 +91,25 @@ struct RbfGen {
     }
     // NI column pairs (c0 + 8*ni, +1) for rows r0 and (unless ONE_ROW) r1: the accumulator layout of one warp tile.
     // Row features are loaded once per dimension for all NI pairs; all loads go through the read-only path.
+    // cooperative: feature values of the panel's 64 columns into shared memory (zero beyond n)
+    __device__ __forceinline__ void stage_cols(int col0, double* cf) const {
+        const int D = s->D;
+        if (!GPSLC_STAGE_COLS || D > CF_DIMS) return;
+        for (int i = threadIdx.x; i < D * NB; i += blockDim.x) {
+            const int d = i >> 6, c = col0 + (i & 63);
+            cf[i] = (c < s->n) ? __ldg(s->feat[d] + c) : 0.0;
+        }
+    }
     template <int NI, bool ONE_ROW>
-    __device__ __forceinline__ void strip(int r0, int r1, int c0, double (&v)[2][NI][2]) const {
+    __device__ __forceinline__ void strip(int r0, int r1, int c0, double (&v)[2][NI][2], const double* cf, int cl) const {
         const int n = s->n;
         if (r1 < n && r0 < n && c0 + 8 * (NI - 1) + 1 < n) {
             double a[2][NI][2];
 #pragma unroll
             for (int ni = 0; ni < NI; ni++) { a[0][ni][0] = 0.0; a[0][ni][1] = 0.0; a[1][ni][0] = 0.0; a[1][ni][1] = 0.0; }
             const int D = s->D;
-#pragma unroll 2
+            const bool staged = GPSLC_STAGE_COLS && (D <= CF_DIMS);
+#pragma unroll 4
             for (int d = 0; d < D; d++) {
                 const double* p = s->feat[d];
                 const double w = s->w[d];
@@ -75,7 +117,13 @@ struct RbfGen {
                 const double z1 = ONE_ROW ? z0 : __ldg(p + r1);
 #pragma unroll
                 for (int ni = 0; ni < NI; ni++) {
-                    const double c0v = __ldg(p + c0 + 8 * ni), c1v = __ldg(p + c0 + 8 * ni + 1);
+                    double c0v, c1v;
+                    if (staged) {
+                        const double2 cc = *reinterpret_cast<const double2*>(cf + d * NB + cl + 8 * ni);
+                        c0v = cc.x; c1v = cc.y;
+                    } else {
+                        c0v = __ldg(p + c0 + 8 * ni); c1v = __ldg(p + c0 + 8 * ni + 1);
+                    }
                     double t;
                     t = z0 - c0v; a[0][ni][0] = fma(t * w, t, a[0][ni][0]);
                     t = z0 - c1v; a[0][ni][1] = fma(t * w, t, a[0][ni][1]);
@@ -89,11 +137,11 @@ struct RbfGen {
 #pragma unroll
             for (int ni = 0; ni < NI; ni++) {
                 const int c = c0 + 8 * ni;
-                v[0][ni][0] = sc * exp(-a[0][ni][0]) + ((r0 == c) ? nz : 0.0);
-                v[0][ni][1] = sc * exp(-a[0][ni][1]) + ((r0 == c + 1) ? nz : 0.0);
+                v[0][ni][0] = sc * exp_neg(a[0][ni][0]) + ((r0 == c) ? nz : 0.0);
+                v[0][ni][1] = sc * exp_neg(a[0][ni][1]) + ((r0 == c + 1) ? nz : 0.0);
                 if (!ONE_ROW) {
-                    v[1][ni][0] = sc * exp(-a[1][ni][0]) + ((r1 == c) ? nz : 0.0);
-                    v[1][ni][1] = sc * exp(-a[1][ni][1]) + ((r1 == c + 1) ? nz : 0.0);
+                    v[1][ni][0] = sc * exp_neg(a[1][ni][0]) + ((r1 == c) ? nz : 0.0);
+                    v[1][ni][1] = sc * exp_neg(a[1][ni][1]) + ((r1 == c + 1) ? nz : 0.0);
                 }
             }
         } else {
@@ -111,10 +159,11 @@ struct RbfGen {
 // strip() for generators that only provide quad()
 #define GPSLC_GENERIC_STRIP                                                                                         \
     template <int NI, bool ONE_ROW>                                                                                 \
-    __device__ __forceinline__ void strip(int r0, int r1, int c0, double (&v)[2][NI][2]) const {                    \
+    __device__ __forceinline__ void strip(int r0, int r1, int c0, double (&v)[2][NI][2], const double*, int) const { \
         _Pragma("unroll") for (int ni = 0; ni < NI; ni++)                                                           \
             quad(r0, r1, c0 + 8 * ni, v[0][ni][0], v[0][ni][1], v[1][ni][0], v[1][ni][1]);                          \
-    }
+    }                                                                                                               \
+    __device__ __forceinline__ void stage_cols(int, double*) const {}
 
 // Dense symmetric matrix read from memory (column-major, lower triangle referenced), for the standalone
 // gpslc_chol_logpdf primitive.
