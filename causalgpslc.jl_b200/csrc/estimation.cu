@@ -190,17 +190,36 @@ sate_kernel(EstArgs a, double* scratch, size_t slot_scratch, double* zbuf, size_
         __syncthreads();
         // Row sums of Kww and Kss give D1 = (Kws - Kww) 1 = a .* rs_ss - rs_ww  and
         // 1'P1 = sum(rs_ww) - 2 a.rs_ss + sum(rs_ss), with a_i = exp(-(T_i - doT)^2 / tyLS^2)  
-        IteGen gen{&spec};
+        // One row per thread, four columns per step with independent accumulators and the branch-free exp, so the FP64 pipe
+        // is throughput- rather than latency-bound; column features are warp-uniform (broadcast) loads.
         double psum = 0.0;
         for (int i = threadIdx.x; i < a.n; i += blockDim.x) {
-            double rs_ww = 0.0, rs_ss = 0.0;
+            double ww[4] = {0.0, 0.0, 0.0, 0.0}, ss[4] = {0.0, 0.0, 0.0, 0.0};
             const double ti = a.T[i];
-            for (int j = 0; j < a.n; j++) {
-                const double b = gen.base(i, j);
-                const double dt = ti - a.T[j];
-                rs_ww += spec.yScale * exp(-(b + dt * spec.wT * dt));
-                rs_ss += spec.yScale * exp(-b);
+            const int D = spec.D;
+            for (int j0 = 0; j0 < a.n; j0 += 4) {
+                double b[4] = {0.0, 0.0, 0.0, 0.0};
+                for (int d = 0; d < D; d++) {
+                    const double* p = spec.feat[d];
+                    const double w = spec.w[d];
+                    const double zi = __ldg(p + i);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int j = min(j0 + u, a.n - 1);
+                        const double t = zi - __ldg(p + j);
+                        b[u] = fma(t * w, t, b[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (j0 + u < a.n) {
+                        const double dt = ti - __ldg(a.T + j0 + u);
+                        ww[u] += spec.yScale * exp_neg(b[u] + dt * spec.wT * dt);
+                        ss[u] += spec.yScale * exp_neg(b[u]);
+                    }
+                }
             }
+            const double rs_ww = (ww[0] + ww[1]) + (ww[2] + ww[3]), rs_ss = (ss[0] + ss[1]) + (ss[2] + ss[3]);
             const double di = ti - spec.doT;
             const double ai = exp(-(di * spec.wT * di));
             d1[i] = ai * rs_ss - rs_ww;

@@ -74,10 +74,13 @@ __device__ inline void build_spec(const ModelDev& m, const ChainDev& c, int chai
                                   double ov_val, RbfSpec* spec) {
     const FactorDef& fd = m.fdef[f];
     const double* theta = c.theta + (size_t)chain * m.n_params;
-    const double* Xm = m.has_xmodel ? c.Xmodel + (size_t)chain * m.n * m.nX : m.X;
+    const double* Xd = m.X + (size_t)chain * m.xstride;     // this chain's observed data (per-chain datasets: SBC-style runs)
+    const double* Td = m.T + (size_t)chain * m.tstride;
+    const double* Yd = m.Y + (size_t)chain * m.tstride;
+    const double* Xm = m.has_xmodel ? c.Xmodel + (size_t)chain * m.n * m.nX : Xd;
     for (int d = threadIdx.x; d < fd.D; d += blockDim.x) {
         const int kind = fd.src_kind[d], idx = fd.src_idx[d];
-        spec->feat[d] = (kind == SRC_U) ? Ubase + (size_t)idx * m.n : (kind == SRC_X) ? Xm + (size_t)idx * m.n : m.T;
+        spec->feat[d] = (kind == SRC_U) ? Ubase + (size_t)idx * m.n : (kind == SRC_X) ? Xm + (size_t)idx * m.n : Td;
         const int p = fd.ls_param[d];
         const double ls = (p == ov_param) ? ov_val : theta[p];
         spec->w[d] = 1.0 / (ls * ls);
@@ -87,9 +90,9 @@ __device__ inline void build_spec(const ModelDev& m, const ChainDev& c, int chai
         spec->n = m.n;
         spec->scale = (fd.scale_param == ov_param) ? ov_val : theta[fd.scale_param];
         spec->noise = (fd.noise_param == ov_param) ? ov_val : theta[fd.noise_param];
-        const double* y = (fd.target_kind == TGT_XCOL) ? m.X + (size_t)fd.target_idx * m.n
-                          : (fd.target_kind == TGT_T)  ? m.T
-                          : (fd.target_kind == TGT_LOGIT) ? c.logitT + (size_t)chain * m.n : m.Y;
+        const double* y = (fd.target_kind == TGT_XCOL) ? Xd + (size_t)fd.target_idx * m.n
+                          : (fd.target_kind == TGT_T)  ? Td
+                          : (fd.target_kind == TGT_LOGIT) ? c.logitT + (size_t)chain * m.n : Yd;
         spec->y[0] = y; spec->y[1] = y;
     }
 }
@@ -382,11 +385,11 @@ __global__ void __launch_bounds__(256) ess_decide_kernel(ModelDev m, ChainDev c,
 // ------------------------------------------------------------------------------------------------ binary treatment
 __device__ __forceinline__ double softplus(double x) { return fmax(x, 0.0) + log1p(exp(-fabs(x))); }
 // sum_i log Bernoulli(T_i; expit(x_i)) (src/model_prior.jl:22-24) in the overflow-safe form
-__device__ inline double block_bernoulli(const ModelDev& m, const double* f, const double* nu, double cs, double sn, double* red) {
+__device__ inline double block_bernoulli(const ModelDev& m, const double* Td, const double* f, const double* nu, double cs, double sn, double* red) {
     double part = 0.0;
     for (int i = threadIdx.x; i < m.n; i += blockDim.x) {
         const double x = f[i] * cs + nu[i] * sn;
-        part += (m.T[i] > 0.5) ? -softplus(-x) : -softplus(x);
+        part += (Td[i] > 0.5) ? -softplus(-x) : -softplus(x);
     }
     return block_sum(part, red);
 }
@@ -421,7 +424,7 @@ logit_prior_kernel(ModelDev m, ChainDev c, int mode, int outer, double* scratch,
             const FactorDef& fd = m.fdef[FT];
             for (int d = threadIdx.x; d < fd.D; d += blockDim.x) {
                 const int kind = fd.src_kind[d], idx = fd.src_idx[d];
-                spec.feat[d] = (kind == SRC_U) ? c.U + ((size_t)chain * m.nU + idx) * m.n : m.X + (size_t)idx * m.n;
+                spec.feat[d] = (kind == SRC_U) ? c.U + ((size_t)chain * m.nU + idx) * m.n : m.X + (size_t)chain * m.xstride + (size_t)idx * m.n;
             }
             __syncthreads();
         }
@@ -485,7 +488,8 @@ ess_logit_kernel(ModelDev m, ChainDev c, int jj, uint32_t it, double* scratch, s
         RbfGen gen{&spec};
         factor_run(gen, NCB, NCB, 2, my_scratch, my_z, sm, pipe);
         const FactorOut o = sm.out;
-        const double bern0 = block_bernoulli(m, f, nu, 1.0, 0.0, red);
+        const double* Td = m.T + (size_t)chain * m.tstride;
+        const double bern0 = block_bernoulli(m, Td, f, nu, 1.0, 0.0, red);
         double logu = 0.0, th = 0.0, tmin = 0.0, tmax = 0.0;
         Stream ss(m.seed, gchain, (uint32_t)m.nU, stream_b(TAG_ESS_SCALAR, it));
         if (threadIdx.x == 0) {
@@ -499,7 +503,7 @@ ess_logit_kernel(ModelDev m, ChainDev c, int jj, uint32_t it, double* scratch, s
         double quad = o.gram[0];
         while (s_done == 0) {
             const double cs = s_cs, sn = s_sn;
-            const double bern = block_bernoulli(m, f, nu, cs, sn, red);
+            const double bern = block_bernoulli(m, Td, f, nu, cs, sn, red);
             __syncthreads();
             if (threadIdx.x == 0) {
                 evals++;
@@ -595,7 +599,7 @@ void sampler_free(Sampler* s) {
 int sampler_create(Ctx* ctx, int loc, int n, int nX, int nU, int binary, const double* X, const double* T, const double* Y,
                    int n_obj, const int* obj_counts, double eps, double cov, const double* pshape, const double* pscale,
                    double drift, int nMH, int nES, int n_chains, unsigned long long seed, int chain_offset, int u_layout_mode,
-                   int ess_rule, int observe_x, Sampler** out) {
+                   int ess_rule, int observe_x, int per_chain_data, Sampler** out) {
     *out = nullptr;
     if (n <= 0 || nX < 0 || nU < 0 || n_chains <= 0 || !T || !Y || (nX > 0 && !X)) return ctx->fail(GPSLC_ERR_ARG, "sampler_create: bad argument");
     if (nU + nX + 1 > DMAX) return ctx->fail(GPSLC_ERR_UNSUPPORTED, "sampler_create: nU + nX + 1 exceeds DMAX");
@@ -712,9 +716,12 @@ int sampler_create(Ctx* ctx, int loc, int n, int nX, int nU, int binary, const d
         return GPSLC_OK;
     };
 #define S_TRY(expr) do { rc = (expr); if (rc) { sampler_free(s); return rc; } } while (0)
-    S_TRY(up_data(X, (size_t)n * nX, &m.X));
-    S_TRY(up_data(T, n, &m.T));
-    S_TRY(up_data(Y, n, &m.Y));
+    const size_t ncopies = per_chain_data ? (size_t)n_chains : 1;
+    m.xstride = per_chain_data ? (size_t)n * nX : 0;
+    m.tstride = per_chain_data ? (size_t)n : 0;
+    S_TRY(up_data(X, ncopies * n * nX, &m.X));
+    S_TRY(up_data(T, ncopies * n, &m.T));
+    S_TRY(up_data(Y, ncopies * n, &m.Y));
     {
         std::vector<int> start(m.n_obj + 1, 0), of(n, 0);
         for (int o = 0; o < m.n_obj; o++) { start[o + 1] = start[o] + obj_counts[o]; for (int i = start[o]; i < start[o + 1]; i++) of[i] = o; }

@@ -34,6 +34,7 @@ struct ModelDev {
     int n, nU, nX, nF, binary, n_params, stride, n_obj, has_xmodel, u_layout_reference, ess_rule;
     double eps, cov, dU, drift;
     const double *X, *T, *Y;
+    size_t xstride, tstride;        // per-chain data offsets (0: one dataset shared by all chains)
     const int *obj_start, *obj_of;
     const FactorDef* fdef;
     const SiteDef* sites;

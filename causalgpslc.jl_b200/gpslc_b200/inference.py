@@ -15,7 +15,7 @@ class GpslcData(ctypes.Structure):
     _fields_ = [("n", ctypes.c_int), ("nX", ctypes.c_int), ("nU", ctypes.c_int), ("binary", ctypes.c_int),
                 ("X", ctypes.c_void_p), ("T", ctypes.c_void_p), ("Y", ctypes.c_void_p),
                 ("n_obj", ctypes.c_int), ("obj_counts", ctypes.c_void_p),
-                ("sigma_u_eps", ctypes.c_double), ("sigma_u_cov", ctypes.c_double)]
+                ("sigma_u_eps", ctypes.c_double), ("sigma_u_cov", ctypes.c_double), ("per_chain_data", ctypes.c_int)]
 
 
 class GpslcPrior(ctypes.Structure):
@@ -80,18 +80,20 @@ def sigma_u_to_counts(SigmaU, eps, cov):
 
 
 def make_structs(priorparams, X, T, Y, nU, counts, nOuter, nMHInner, nESInner, n_chains, seed, chain_offset,
-                 u_layout_mode, ess_rule, observe_x):
+                 u_layout_mode, ess_rule, observe_x, per_chain_data=False):
+    """per_chain_data: T, Y are [n_chains, n] and X is [n_chains, n, nX] (one dataset per chain)."""
     T = np.asarray(T)
     binary = T.dtype == np.bool_
     keep = {}
     keep["T"] = np.ascontiguousarray(T, dtype=np.float64)
     keep["Y"] = np.ascontiguousarray(Y, dtype=np.float64)
-    n = keep["T"].shape[0]
+    n = keep["T"].shape[-1]
     nX = 0
     if X is not None:
         X = np.asarray(X, dtype=np.float64)
-        nX = X.shape[1]
-        keep["X"] = np.asfortranarray(X)
+        nX = X.shape[-1]
+        # each dataset column-major n x nX
+        keep["X"] = np.ascontiguousarray(np.swapaxes(X, -1, -2)) if per_chain_data else np.asfortranarray(X)
     d = GpslcData()
     d.n, d.nX, d.nU, d.binary = n, nX, int(nU or 0), int(binary)
     d.X = keep["X"].ctypes.data if nX else None
@@ -101,6 +103,7 @@ def make_structs(priorparams, X, T, Y, nU, counts, nOuter, nMHInner, nESInner, n
         keep["counts"] = np.ascontiguousarray(counts, dtype=np.int32)
         d.n_obj = len(counts)
         d.obj_counts = keep["counts"].ctypes.data
+    d.per_chain_data = int(bool(per_chain_data))
     d.sigma_u_eps = float(priorparams["sigmaUNoise"])
     d.sigma_u_cov = float(priorparams["sigmaUCov"])
     p = GpslcPrior()
@@ -119,13 +122,14 @@ class ChainSampler:
     """gpslc_sampler: n_chains independent chains resident on one GPU."""
 
     def __init__(self, priorparams, X, T, Y, nU, counts, nOuter, nMHInner, nESInner, n_chains=1, seed=0, chain_offset=0,
-                 u_layout_mode=0, ess_rule=0, observe_x=0, ctx=None):
+                 u_layout_mode=0, ess_rule=0, observe_x=0, ctx=None, per_chain_data=False):
         from .kernel import default_context
         self.ctx = ctx or default_context()
         lib = self.ctx.lib
         _bind(lib)
         self.d, self.p, self.o, self._keep = make_structs(priorparams, X, T, Y, nU, counts, nOuter, nMHInner, nESInner,
-                                                          n_chains, seed, chain_offset, u_layout_mode, ess_rule, observe_x)
+                                                          n_chains, seed, chain_offset, u_layout_mode, ess_rule, observe_x,
+                                                          per_chain_data)
         h = ctypes.c_void_p()
         self.ctx.check(lib.gpslc_sampler_create(self.ctx.h, HOST, ctypes.byref(self.d), ctypes.byref(self.p),
                                                 ctypes.byref(self.o), ctypes.byref(h)))

@@ -18,6 +18,7 @@ struct GpslcData            # include/gpslc.h: gpslc_data
     X::Ptr{Cdouble}; T::Ptr{Cdouble}; Y::Ptr{Cdouble}
     n_obj::Cint; obj_counts::Ptr{Cint}
     sigma_u_eps::Cdouble; sigma_u_cov::Cdouble
+    per_chain_data::Cint
 end
 struct GpslcPrior           # gpslc_prior
     shape::NTuple{13,Cdouble}; scale::NTuple{13,Cdouble}; drift::Cdouble
@@ -102,7 +103,7 @@ function Posterior(priorparams, X, T, Y, nU, nOuter, nMHInner, nESInner; n_chain
     out = Array{Float64}(undef, stride, n_chains, nOuter)          # column-major == C [nOuter][n_chains][stride]
     GC.@preserve Tf Xf Yf counts out begin
         d = GpslcData(n, nX, nu, binary, nX > 0 ? pointer(Xf) : C_NULL, pointer(Tf), pointer(Yf), length(counts),
-                      nu > 0 ? pointer(counts) : C_NULL, priorparams["sigmaUNoise"], priorparams["sigmaUCov"])
+                      nu > 0 ? pointer(counts) : C_NULL, priorparams["sigmaUNoise"], priorparams["sigmaUCov"], 0)
         o = GpslcOpts(nOuter, something(nMHInner, 0), something(nESInner, 0), n_chains, seed, chain_offset, u_layout_mode, ess_rule, observe_x)
         check(ccall((:gpslc_posterior, LIB[]), Cint,
                     (Ptr{Cvoid}, Ref{GpslcData}, Ref{GpslcPrior}, Ref{GpslcOpts}, Ptr{Cdouble}, Ptr{Culonglong}, Ptr{Culonglong}),
@@ -132,7 +133,7 @@ end
 
 function data_struct(g, Tf, Xf, Yf)
     nX = g.X === nothing ? 0 : size(g.X, 2); nU = g.hyperparams.nU === nothing ? 0 : g.hyperparams.nU
-    GpslcData(length(Yf), nX, nU, eltype(g.T) == Bool, nX > 0 ? pointer(Xf) : C_NULL, pointer(Tf), pointer(Yf), 0, C_NULL, 0.0, 0.0)
+    GpslcData(length(Yf), nX, nU, eltype(g.T) == Bool, nX > 0 ? pointer(Xf) : C_NULL, pointer(Tf), pointer(Yf), 0, C_NULL, 0.0, 0.0, 0)
 end
 
 """

@@ -99,6 +99,8 @@ typedef struct {
     const int* obj_counts; /* their sizes, in row order (rows sorted by obj as prepareData does, src/data.jl:25) */
     double sigma_u_eps;    /* 1e-13 by default (src/hyperparameters.jl:66) */
     double sigma_u_cov;    /* 1.0 by default  (src/hyperparameters.jl:67) */
+    int per_chain_data;    /* 0: X, T, Y are one dataset shared by all chains (the reference's case); 1: X, T, Y hold n_chains
+                              datasets back to back (chain-major) — simulation-based calibration runs, test/sbc.jl shape */
 } gpslc_data;
 
 /* InvGamma(shape, scale) priors of src/hyperparameters.jl:39-65 in the order
