@@ -253,7 +253,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             run, Ssites = cpu_sample()
             run(0, 2)
-            nsite = 12
+            nsite = Ssites                      # one full sweep of one chain (about 10-15 s of CPU work)
             tc = run(2, nsite)
             line["cpu_baseline"] = {"value": (nsite / Ssites) / tc, "unit": "sweeps/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"{nsite} of {Ssites} single-site MH updates of one sweep of one chain at the c3 shape, "

@@ -14,8 +14,9 @@ struct Ctx {
     std::string last_error;
     // factor workspaces: one slot per resident CTA
     int slots = 0;
-    size_t slot_scratch_d = 0;   // doubles of L scratch per slot
+    size_t slot_scratch_d = 0;   // doubles of L scratch per slot (stride used by the current launch)
     size_t slot_z_d = 0;         // doubles of z/w scratch per slot
+    size_t scratch_cap_d = 0, z_cap_d = 0;   // allocated capacities (doubles)
     double* scratch = nullptr;
     double* zbuf = nullptr;
     unsigned int* counter = nullptr;  // work-queue counters (device)
@@ -34,7 +35,8 @@ struct Ctx {
         if (_e != cudaSuccess) return (ctx)->cuda_fail(_e, #call);           \
     } while (0)
 
-// make sure every slot can hold an NRB x NCB block matrix
-int ensure_workspace(Ctx* ctx, int NRB, int NCB);
+// Reserve factor workspaces for `tasks` independent NRB x NCB block matrices and return the grid size to launch: one slot per
+// resident CTA, fewer when there are fewer tasks or when the slots would not fit in free HBM (large n).
+int ensure_workspace(Ctx* ctx, int NRB, int NCB, long long tasks, int* grid);
 
 }  // namespace gpslc

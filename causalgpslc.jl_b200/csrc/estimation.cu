@@ -269,12 +269,12 @@ sate_kernel(EstArgs a, double* scratch, size_t slot_scratch, double* zbuf, size_
 
 int launch_ite(Ctx* ctx, const EstArgs& a) {
     const int NCB = 2 * ceil_div(a.n, NB);
-    GP_TRY(ensure_workspace(ctx, NCB, NCB));
+    int grid = 0;
+    GP_TRY(ensure_workspace(ctx, NCB, NCB, (long long)a.n_doT * a.n_chains * a.R, &grid));
     GP_CUDA(ctx, cudaFuncSetAttribute(ite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
     GP_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, sizeof(unsigned int), ctx->stream));
     const long long total = (long long)a.n_doT * a.n_chains * a.R;
     if (total == 0) return GPSLC_OK;
-    const int grid = (int)(total < ctx->slots ? total : ctx->slots);
     double* xi = nullptr;
     GP_CUDA(ctx, cudaMalloc(&xi, (size_t)grid * 4 * a.n * sizeof(double)));
     ite_kernel<<<grid, FTHREADS, sizeof(FactorSmem), ctx->stream>>>(a, ctx->scratch, ctx->slot_scratch_d, ctx->zbuf, ctx->slot_z_d, xi, ctx->counter);
@@ -289,12 +289,12 @@ int launch_ite(Ctx* ctx, const EstArgs& a) {
 
 int launch_sate(Ctx* ctx, const EstArgs& a) {
     const int NCB = ceil_div(a.n, NB);
-    GP_TRY(ensure_workspace(ctx, NCB, NCB));
+    int grid = 0;
+    GP_TRY(ensure_workspace(ctx, NCB, NCB, (long long)a.n_doT * a.n_chains * a.R, &grid));
     GP_CUDA(ctx, cudaFuncSetAttribute(sate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
     GP_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, sizeof(unsigned int), ctx->stream));
     const long long total = (long long)a.n_doT * a.n_chains * a.R;
     if (total == 0) return GPSLC_OK;
-    const int grid = (int)(total < ctx->slots ? total : ctx->slots);
     double* d1 = nullptr;
     GP_CUDA(ctx, cudaMalloc(&d1, (size_t)grid * a.n * sizeof(double)));
     sate_kernel<<<grid, FTHREADS, sizeof(FactorSmem), ctx->stream>>>(a, ctx->scratch, ctx->slot_scratch_d, ctx->zbuf, ctx->slot_z_d, d1, ctx->counter);

@@ -6,7 +6,7 @@
 
 namespace gpslc {
 
-int ensure_workspace(Ctx* ctx, int NRB, int NCB) {
+int ensure_workspace(Ctx* ctx, int NRB, int NCB, long long tasks, int* grid_out) {
     const size_t need = scratch_doubles(NRB, NCB);
     const size_t needz = (size_t)2 * MAXRHS * NCB * NB;
     if (ctx->slots == 0) {
@@ -14,19 +14,33 @@ int ensure_workspace(Ctx* ctx, int NRB, int NCB) {
         const int per = (e && atoi(e) > 0) ? atoi(e) : 2;
         ctx->slots = per * ctx->num_sms;
     }
-    if (need > ctx->slot_scratch_d) {
+    long long grid = tasks < ctx->slots ? tasks : ctx->slots;
+    if (grid < 1) grid = 1;
+    if ((size_t)grid * need > ctx->scratch_cap_d) {
+        // bound the slot count by what fits in HBM (n = 8192 augmented: ~1 GiB per slot)
+        size_t free_b = 0, total_b = 0;
+        GP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+        const size_t avail = (size_t)(0.8 * (double)(free_b + ctx->scratch_cap_d * sizeof(double)));
+        long long fit = (long long)(avail / ((need + needz) * sizeof(double)));
+        if (fit < 1) return ctx->fail(GPSLC_ERR_CUDA, "not enough device memory for one factor workspace");
+        if (grid > fit) grid = fit;
+    }
+    if ((size_t)grid * need > ctx->scratch_cap_d) {
         if (ctx->scratch) cudaFree(ctx->scratch);
-        ctx->scratch = nullptr;
-        GP_CUDA(ctx, cudaMalloc(&ctx->scratch, need * ctx->slots * sizeof(double)));
-        ctx->slot_scratch_d = need;
+        ctx->scratch = nullptr; ctx->scratch_cap_d = 0;
+        GP_CUDA(ctx, cudaMalloc(&ctx->scratch, (size_t)grid * need * sizeof(double)));
+        ctx->scratch_cap_d = (size_t)grid * need;
     }
-    if (needz > ctx->slot_z_d) {
+    if ((size_t)grid * needz > ctx->z_cap_d) {
         if (ctx->zbuf) cudaFree(ctx->zbuf);
-        ctx->zbuf = nullptr;
-        GP_CUDA(ctx, cudaMalloc(&ctx->zbuf, needz * ctx->slots * sizeof(double)));
-        ctx->slot_z_d = needz;
+        ctx->zbuf = nullptr; ctx->z_cap_d = 0;
+        GP_CUDA(ctx, cudaMalloc(&ctx->zbuf, (size_t)grid * needz * sizeof(double)));
+        ctx->z_cap_d = (size_t)grid * needz;
     }
+    ctx->slot_scratch_d = need;
+    ctx->slot_z_d = needz;
     if (!ctx->counter) GP_CUDA(ctx, cudaMalloc(&ctx->counter, 64 * sizeof(unsigned int)));
+    *grid_out = (int)grid;
     return GPSLC_OK;
 }
 
@@ -174,12 +188,12 @@ static int launch_batched(Ctx* ctx, int batch, int n, const double* K, int ld, c
                           const double* feat, size_t feat_stride, const double* w, const double* scale,
                           const double* noise, double* logpdf, double* logdet, double* quad, int* info) {
     const int NCB = ceil_div(n, NB);
-    int rc = ensure_workspace(ctx, NCB, NCB);
+    int grid = 0;
+    int rc = ensure_workspace(ctx, NCB, NCB, batch, &grid);
     if (rc) return rc;
     auto kern = batched_logpdf_kernel<FUSED>;
     GP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
     GP_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, sizeof(unsigned int), ctx->stream));
-    const int grid = batch < ctx->slots ? batch : ctx->slots;
     kern<<<grid, FTHREADS, sizeof(FactorSmem), ctx->stream>>>(batch, n, K, ld, y, y_shared, D, feat, feat_stride, w, scale,
                                                              noise, ctx->scratch, ctx->slot_scratch_d, ctx->zbuf,
                                                              ctx->slot_z_d, ctx->counter, logpdf, logdet, quad, info);

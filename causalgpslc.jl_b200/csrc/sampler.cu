@@ -769,7 +769,7 @@ int sampler_create(Ctx* ctx, int loc, int n, int nX, int nU, int binary, const d
     cudaMemsetAsync(c.info, 0, C * sizeof(int), ctx->stream);
     cudaMemsetAsync(c.infoP, 0, C * sizeof(int), ctx->stream);
     const int NCB = ceil_div(n, NB);
-    S_TRY(ensure_workspace(ctx, NCB, NCB));
+    { int g0 = 0; S_TRY(ensure_workspace(ctx, NCB, NCB, (long long)n_chains * (nX + 2), &g0)); }
 #undef S_TRY
     *out = s;
     return GPSLC_OK;
@@ -781,7 +781,8 @@ static int launch_eval(Sampler* s, const int* list, const unsigned int* n_list_d
     GP_CUDA(ctx, cudaFuncSetAttribute(eval_factors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
     GP_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, sizeof(unsigned int), ctx->stream));
     const long long tasks = (long long)n_list_host * s->n_exist;
-    const int grid = (int)(tasks < ctx->slots ? tasks : ctx->slots);
+    int grid = 0;
+    GP_TRY(ensure_workspace(ctx, ceil_div(s->m.n, NB), ceil_div(s->m.n, NB), tasks, &grid));
     eval_factors_kernel<<<grid, FTHREADS, sizeof(FactorSmem), ctx->stream>>>(s->m, s->c, list, n_list_dev, s->m.n_chains, s->d_exist,
                                                                            s->n_exist, proposed, ctx->scratch, ctx->slot_scratch_d,
                                                                            ctx->zbuf, ctx->slot_z_d, ctx->counter);
@@ -794,7 +795,8 @@ static int launch_logit_prior(Sampler* s, int mode, int outer) {
     Ctx* ctx = s->ctx;
     GP_CUDA(ctx, cudaFuncSetAttribute(logit_prior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
     GP_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, sizeof(unsigned int), ctx->stream));
-    const int grid = s->m.n_chains < ctx->slots ? s->m.n_chains : ctx->slots;
+    int grid = 0;
+    GP_TRY(ensure_workspace(ctx, ceil_div(s->m.n, NB), ceil_div(s->m.n, NB), s->m.n_chains, &grid));
     if (!s->xibuf) { GP_CUDA(ctx, cudaMalloc(&s->xibuf, (size_t)ctx->slots * 4 * s->m.n * sizeof(double))); s->owned.push_back(s->xibuf); }
     logit_prior_kernel<<<grid, FTHREADS, sizeof(FactorSmem), ctx->stream>>>(s->m, s->c, mode, outer, ctx->scratch, ctx->slot_scratch_d,
                                                                           ctx->zbuf, ctx->slot_z_d, s->xibuf, ctx->counter);
@@ -807,7 +809,8 @@ static int launch_ess_logit(Sampler* s, int jj, uint32_t it) {
     Ctx* ctx = s->ctx;
     GP_CUDA(ctx, cudaFuncSetAttribute(ess_logit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
     GP_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, sizeof(unsigned int), ctx->stream));
-    const int grid = s->m.n_chains < ctx->slots ? s->m.n_chains : ctx->slots;
+    int grid = 0;
+    GP_TRY(ensure_workspace(ctx, ceil_div(s->m.n, NB), ceil_div(s->m.n, NB), s->m.n_chains, &grid));
     ess_logit_kernel<<<grid, FTHREADS, sizeof(FactorSmem), ctx->stream>>>(s->m, s->c, jj, it, ctx->scratch, ctx->slot_scratch_d, ctx->zbuf,
                                                                         ctx->slot_z_d, ctx->counter);
     ctx->launches++;
@@ -859,7 +862,8 @@ int sampler_mh(Sampler* s, int outer, int j0, int j1) {
     GP_CUDA(ctx, cudaFuncSetAttribute(mh_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
     GP_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, sizeof(unsigned int), ctx->stream));
     const long long tasks = (long long)s->m.n_chains * s->m.n_lanes;
-    const int grid = (int)(tasks < ctx->slots ? tasks : ctx->slots);
+    int grid = 0;
+    GP_TRY(ensure_workspace(ctx, ceil_div(s->m.n, NB), ceil_div(s->m.n, NB), tasks, &grid));
     mh_lanes_kernel<<<grid, FTHREADS, sizeof(FactorSmem), ctx->stream>>>(s->m, s->c, s->d_lane_order, outer, j0, j1, ctx->scratch,
                                                                        ctx->slot_scratch_d, ctx->zbuf, ctx->slot_z_d, ctx->counter);
     ctx->launches++;
