@@ -36,7 +36,8 @@ struct Ctx {
     } while (0)
 
 // Reserve factor workspaces for `tasks` independent NRB x NCB block matrices and return the grid size to launch: one slot per
-// resident CTA, fewer when there are fewer tasks or when the slots would not fit in free HBM (large n).
-int ensure_workspace(Ctx* ctx, int NRB, int NCB, long long tasks, int* grid);
+// resident CTA, fewer when there are fewer tasks or when the slots would not fit in free HBM (large n). With team > 1 (cluster
+// launches, factor.cuh) a slot of L scratch serves a whole team and *grid is the number of teams.
+int ensure_workspace(Ctx* ctx, int NRB, int NCB, long long tasks, int* grid, int team = 1);
 
 }  // namespace gpslc

@@ -47,18 +47,18 @@ struct IteGen {
         const double b = base(i, j);
         const double ti = s->T[i], tj = s->T[j];
         const double dt = ti - tj, tt = dt * s->wT * dt;
+        // same factored form as strip(): yScale * exp(-b) * g
+        const double eb = s->yScale * exp_neg(b), eij = exp_neg(tt);
         if (!r2) {  // Kp
-            double v = s->yScale * exp(-(b + tt));
+            double v = eb * eij;
             if (i == j) v += s->yNoise;
             return v;
         }
         const double di = ti - s->doT, dj = tj - s->doT;
-        if (!c2) {  // D'[i][j] = Kws[j][i] - Kww[j][i]
-            return s->yScale * exp(-(b + dj * s->wT * dj)) - s->yScale * exp(-(b + tt));
-        }
-        // P + jitter I
-        double v = s->yScale * exp(-(b + tt)) - s->yScale * exp(-(b + di * s->wT * di)) - s->yScale * exp(-(b + dj * s->wT * dj)) +
-                   s->yScale * exp(-b);
+        const double aj = exp_neg(dj * s->wT * dj);
+        if (!c2) return eb * (aj - eij);   // D'[i][j] = Kws[j][i] - Kww[j][i]
+        const double ai = exp_neg(di * s->wT * di);
+        double v = eb * (((eij - ai) - aj) + 1.0);   // P + jitter I
         if (i == j) v += s->jitter;
         return v;
     }
@@ -66,7 +66,92 @@ struct IteGen {
         v00 = one(r0, c); v01 = one(r0, c + 1); v10 = one(r1, c); v11 = one(r1, c + 1);
     }
     __device__ __forceinline__ double rhs(int which, int r) const { return (r < s->n) ? s->Y[r] : 0.0; }
-    GPSLC_GENERIC_STRIP
+    // Column features of the panel (zero beyond n): the D shared dimensions, then T_j, then a_j = exp(-(T_j - doT)^2 / tyLS^2).
+    __device__ __forceinline__ void stage_cols(int col0, double* cf) const {
+        const int D = s->D;
+        if (D + 2 > CF_DIMS) return;
+        const int j0 = (col0 >= s->npad) ? col0 - s->npad : col0;
+        for (int i = threadIdx.x; i < (D + 2) * NB; i += blockDim.x) {
+            const int d = i >> 6, c = j0 + (i & 63);
+            double v = 0.0;
+            if (c < s->n) {
+                if (d < D) v = __ldg(s->feat[d] + c);
+                else {
+                    v = __ldg(s->T + c);
+                    if (d == D + 1) { const double dj = v - s->doT; v = exp_neg(dj * s->wT * dj); }
+                }
+            }
+            cf[i] = v;
+        }
+    }
+    // Every entry of the augmented matrix is yScale * exp(-b_ij) * g, with b the shared-dimension distance and
+    //   Kp: g = e_ij            D': g = a_j - e_ij            P: g = e_ij - a_i - a_j + 1,     e_ij = exp(-(T_i - T_j)^2 / tyLS^2)
+    // (src/likelihood.jl:24-28 builds Kww, Kws, Kss from the same five log-kernels), so a strip costs two exponentials per entry.
+    // A strip never straddles the block boundary (npad is a multiple of the panel width).
+    template <int NI, bool ONE_ROW>
+    __device__ __forceinline__ void strip(int r0, int r1, int c0, double (&v)[2][NI][2], const double* cf, int cl) const {
+        const int n = s->n, np = s->npad, D = s->D;
+        const bool r2 = r0 >= np, c2 = c0 >= np;
+        const int i0 = r2 ? r0 - np : r0, i1 = r2 ? r1 - np : r1, j0 = c2 ? c0 - np : c0;
+        if (D + 2 <= CF_DIMS && i0 < n && i1 < n && j0 + 8 * (NI - 1) + 1 < n) {
+            double a[2][NI][2];
+#pragma unroll
+            for (int ni = 0; ni < NI; ni++) { a[0][ni][0] = 0.0; a[0][ni][1] = 0.0; a[1][ni][0] = 0.0; a[1][ni][1] = 0.0; }
+#pragma unroll 4
+            for (int d = 0; d < D; d++) {
+                const double* p = s->feat[d];
+                const double w = s->w[d];
+                const double z0 = __ldg(p + i0);
+                const double z1 = ONE_ROW ? z0 : __ldg(p + i1);
+#pragma unroll
+                for (int ni = 0; ni < NI; ni++) {
+                    const double2 cc = *reinterpret_cast<const double2*>(cf + d * NB + cl + 8 * ni);
+                    double t;
+                    t = z0 - cc.x; a[0][ni][0] = fma(t * w, t, a[0][ni][0]);
+                    t = z0 - cc.y; a[0][ni][1] = fma(t * w, t, a[0][ni][1]);
+                    if (!ONE_ROW) {
+                        t = z1 - cc.x; a[1][ni][0] = fma(t * w, t, a[1][ni][0]);
+                        t = z1 - cc.y; a[1][ni][1] = fma(t * w, t, a[1][ni][1]);
+                    }
+                }
+            }
+            const double sc = s->yScale, wT = s->wT;
+            const double t0 = __ldg(s->T + i0), t1 = ONE_ROW ? t0 : __ldg(s->T + i1);
+            double ai0 = 0.0, ai1 = 0.0;
+            if (r2 && c2) {
+                const double d0 = t0 - s->doT, d1 = t1 - s->doT;
+                ai0 = exp_neg(d0 * wT * d0); ai1 = ONE_ROW ? ai0 : exp_neg(d1 * wT * d1);
+            }
+            const double diag = c2 ? s->jitter : s->yNoise;
+#pragma unroll
+            for (int ni = 0; ni < NI; ni++) {
+                const double2 tc = *reinterpret_cast<const double2*>(cf + D * NB + cl + 8 * ni);
+                const double2 ac = *reinterpret_cast<const double2*>(cf + (D + 1) * NB + cl + 8 * ni);
+#pragma unroll
+                for (int rr = 0; rr < (ONE_ROW ? 1 : 2); rr++) {
+                    const double ti = rr ? t1 : t0, ai = rr ? ai1 : ai0;
+                    const int r = rr ? r1 : r0;
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const double tj = e ? tc.y : tc.x, aj = e ? ac.y : ac.x;
+                        const double dt = ti - tj;
+                        const double eij = exp_neg(dt * wT * dt);
+                        double gfac;
+                        if (!r2) gfac = eij;
+                        else if (!c2) gfac = aj - eij;
+                        else gfac = ((eij - ai) - aj) + 1.0;
+                        double val = sc * exp_neg(a[rr][ni][e]) * gfac;
+                        if (r == c0 + 8 * ni + e && r2 == c2) val += diag;
+                        v[rr][ni][e] = val;
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int ni = 0; ni < NI; ni++)
+                quad(r0, r1, c0 + 8 * ni, v[0][ni][0], v[0][ni][1], v[1][ni][0], v[1][ni][1]);
+        }
+    }
 };
 
 
@@ -94,7 +179,10 @@ __device__ inline void fill_ite_spec(const EstArgs& a, const double* rec, double
     }
 }
 
-// one task = (doT d, chain c, retained sample r): augmented Cholesky, MeanITE, optional CovITE, ITE draws
+// one task = (doT d, chain c, retained sample r): augmented Cholesky, MeanITE, optional CovITE, ITE draws.
+// TEAM = 0: one CTA per task, tasks handed out from an atomic counter. TEAM = 1: one thread-block cluster per task (few large
+// tasks, c5 of BASELINE.json); scratch is indexed by cluster, z / xi buffers by CTA, tasks are dealt out round-robin.
+template <int TEAM>
 __global__ void __launch_bounds__(FTHREADS, 2)
 ite_kernel(EstArgs a, double* scratch, size_t slot_scratch, double* zbuf, size_t slot_z, double* xibuf, unsigned int* counter) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -104,14 +192,21 @@ ite_kernel(EstArgs a, double* scratch, size_t slot_scratch, double* zbuf, size_t
     factor_smem_init(sm);
     Pipe pipe{0, 0};
     const int NCB1 = ceil_div(a.n, NB), NCB = 2 * NCB1, npad = NCB1 * NB;
-    double* my_scratch = scratch + (size_t)blockIdx.x * slot_scratch;
+    const int trank = TEAM ? (int)cluster_rank() : 0, tsize = TEAM ? (int)cluster_size() : 1;
+    const unsigned int team = TEAM ? cluster_id_x() : blockIdx.x, nteams = TEAM ? cluster_count_x() : gridDim.x;
+    double* my_scratch = scratch + (size_t)team * slot_scratch;
     double* my_z = zbuf + (size_t)blockIdx.x * slot_z;
     double* xi = xibuf + (size_t)blockIdx.x * 4 * a.n;
     const unsigned int total = (unsigned)a.n_doT * a.n_chains * a.R;
-    for (;;) {
-        if (threadIdx.x == 0) job = atomicAdd(counter, 1u);
-        __syncthreads();
-        const unsigned int t = job;
+    for (unsigned int round = 0;; round++) {
+        unsigned int t;
+        if constexpr (TEAM != 0) {
+            t = team + round * nteams;
+        } else {
+            if (threadIdx.x == 0) job = atomicAdd(counter, 1u);
+            __syncthreads();
+            t = job;
+        }
         if (t >= total) break;
         const int r = t % a.R, c = (t / a.R) % a.n_chains, d = t / (a.R * a.n_chains);
         const double* rec = a.samples + ((size_t)a.ret_idx[r] * a.n_chains + c) * a.stride;
@@ -119,14 +214,14 @@ ite_kernel(EstArgs a, double* scratch, size_t slot_scratch, double* zbuf, size_t
         __syncthreads();
         IteGen gen{&spec};
         double* cov = a.cov_out ? a.cov_out + (size_t)t * a.n * a.n : nullptr;
-        factor_run(gen, NCB, NCB, 1, my_scratch, my_z, sm, pipe, NCB1, cov, a.n);
+        factor_run<IteGen, TEAM, true>(gen, NCB, NCB, 1, my_scratch, my_z, sm, pipe, NCB1, cov, a.n);
         const int info = sm.out.info;
-        if (threadIdx.x == 0 && a.info) a.info[t] = info;
-        // MeanITE = -(pre-solve residual of the second block)
+        if (threadIdx.x == 0 && trank == 0 && a.info) a.info[t] = info;
+        // MeanITE = -(pre-solve residual of the second block); every CTA of a team holds the same residual in its own zbuf
         const double* wres = my_z + (size_t)MAXRHS * (2 * npad) + npad;
-        if (a.mean_out)
+        if (a.mean_out && trank == 0)
             for (int i = threadIdx.x; i < a.n; i += blockDim.x) a.mean_out[(size_t)t * a.n + i] = -wres[i];
-        // draws: MeanITE + L22 xi   (src/estimation.jl:95-109; one factor serves all spp draws)
+        // draws: MeanITE + L22 xi   (src/estimation.jl:95-109; one factor serves all spp draws); rows are split across the team
         if (a.ite_out && a.spp > 0) {
             const unsigned gchain = (unsigned)(a.chain0 + c);
             for (int s0 = 0; s0 < a.spp; s0 += 4) {
@@ -138,7 +233,7 @@ ite_kernel(EstArgs a, double* scratch, size_t slot_scratch, double* zbuf, size_t
                     xi[(size_t)s * a.n + col] = st.normal_at(col);
                 }
                 __syncthreads();
-                for (int i = threadIdx.x; i < a.n; i += blockDim.x) {
+                for (int i = trank * blockDim.x + threadIdx.x; i < a.n; i += tsize * blockDim.x) {
                     double accv[4] = {0.0, 0.0, 0.0, 0.0};
                     const int I = NCB1 + (i >> 6), ri = i & 63;
                     for (int jb = 0; jb <= (i >> 6); jb++) {
@@ -159,7 +254,9 @@ ite_kernel(EstArgs a, double* scratch, size_t slot_scratch, double* zbuf, size_t
                 }
             }
         }
-        __syncthreads();
+        // the next task overwrites the shared scratch: wait until every CTA of the team has finished reading L22
+        if constexpr (TEAM != 0) cluster_barrier();
+        else __syncthreads();
     }
 }
 
@@ -267,19 +364,50 @@ sate_kernel(EstArgs a, double* scratch, size_t slot_scratch, double* zbuf, size_
     }
 }
 
+// Team size for `tasks` independent factorizations with NCB block columns: the largest power of two (<= 8, the portable cluster
+// limit) that still leaves every task a team of its own among the resident CTAs. GPSLC_TEAM overrides (development knob).
+static int pick_team(Ctx* ctx, long long tasks, int NCB) {
+    if (const char* e = getenv("GPSLC_TEAM")) { const int g = atoi(e); if (g == 1 || g == 2 || g == 4 || g == 8) return g; }
+    const long long resident = 2LL * ctx->num_sms;
+    int g = 1;
+    while (g < 8 && tasks * (2 * g) <= resident && 4 * (2 * g) <= NCB) g *= 2;
+    return g;
+}
+
 int launch_ite(Ctx* ctx, const EstArgs& a) {
     const int NCB = 2 * ceil_div(a.n, NB);
-    int grid = 0;
-    GP_TRY(ensure_workspace(ctx, NCB, NCB, (long long)a.n_doT * a.n_chains * a.R, &grid));
-    GP_CUDA(ctx, cudaFuncSetAttribute(ite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
-    GP_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, sizeof(unsigned int), ctx->stream));
     const long long total = (long long)a.n_doT * a.n_chains * a.R;
     if (total == 0) return GPSLC_OK;
+    int team = pick_team(ctx, total, NCB);
+    int grid = 0;   // number of scratch slots == number of teams
+    GP_TRY(ensure_workspace(ctx, NCB, NCB, total, &grid, team));
+    GP_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, sizeof(unsigned int), ctx->stream));
     double* xi = nullptr;
-    GP_CUDA(ctx, cudaMalloc(&xi, (size_t)grid * 4 * a.n * sizeof(double)));
-    ite_kernel<<<grid, FTHREADS, sizeof(FactorSmem), ctx->stream>>>(a, ctx->scratch, ctx->slot_scratch_d, ctx->zbuf, ctx->slot_z_d, xi, ctx->counter);
+    cudaError_t e = cudaSuccess;
+    if (team == 1) {
+        GP_CUDA(ctx, cudaFuncSetAttribute(ite_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
+        GP_CUDA(ctx, cudaMalloc(&xi, (size_t)grid * 4 * a.n * sizeof(double)));
+        ite_kernel<0><<<grid, FTHREADS, sizeof(FactorSmem), ctx->stream>>>(a, ctx->scratch, ctx->slot_scratch_d, ctx->zbuf, ctx->slot_z_d, xi,
+                                                                         ctx->counter);
+        e = cudaGetLastError();
+    } else {
+        GP_CUDA(ctx, cudaFuncSetAttribute(ite_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = team; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.blockDim = dim3(FTHREADS); cfg.dynamicSmemBytes = sizeof(FactorSmem); cfg.stream = ctx->stream;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cfg.gridDim = dim3(grid * team);
+        int max_clusters = 0;
+        GP_CUDA(ctx, cudaOccupancyMaxActiveClusters(&max_clusters, ite_kernel<1>, &cfg));
+        if (max_clusters < 1) return ctx->fail(GPSLC_ERR_CUDA, "ite_kernel: no resident cluster of the requested size");
+        if (grid > max_clusters) grid = max_clusters;   // fewer teams than slots: the teams loop over the tasks
+        cfg.gridDim = dim3(grid * team);
+        GP_CUDA(ctx, cudaMalloc(&xi, (size_t)grid * team * 4 * a.n * sizeof(double)));
+        e = cudaLaunchKernelEx(&cfg, ite_kernel<1>, a, ctx->scratch, ctx->slot_scratch_d, ctx->zbuf, ctx->slot_z_d, xi, ctx->counter);
+    }
     ctx->launches++;
-    cudaError_t e = cudaGetLastError();
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
     cudaFree(xi);
     if (e != cudaSuccess) return ctx->cuda_fail(e, "ite_kernel");

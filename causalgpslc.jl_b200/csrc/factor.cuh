@@ -84,6 +84,27 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
+// Team mode (TEAM = 1): the CTAs of one thread-block cluster factor ONE matrix together (few large matrices, e.g. the
+// n = 8192 counterfactual sweep, where one CTA per matrix would leave most SMs idle). The L scratch in global memory is shared by
+// the team; the diagonal tile, P2 and the forward solve are computed redundantly by every CTA (each keeps its own Linv, z and
+// partial sums), the row blocks below the diagonal are split across the team, and one cluster barrier (release/acquire) per
+// panel publishes the new L blocks.
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_count_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// end-of-phase synchronisation: generic-proxy writes (shared workspace, global L blocks) are ordered before later async-proxy
+// (TMA bulk) reads, by this CTA or — in team mode — by any CTA of the cluster
+template <int TEAM>
+__device__ __forceinline__ void team_sync() {
+    fence_proxy_async();
+    if constexpr (TEAM != 0) { cluster_barrier(); fence_proxy_async(); }
+    else __syncthreads();
+}
+
 // FP64 tensor-core MMA (SASS: DMMA.8x8x4). A: lane holds A[lane/4][lane%4]; B: lane holds B[lane%4][lane/4];
 // C/D: lane holds rows lane/4, cols 2*(lane%4)+{0,1}.
 __device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
@@ -249,15 +270,17 @@ struct Pipe { uint32_t produced; uint32_t consumed; };
 //   void quad(int r0, int r1, int c, double& v00, double& v01, double& v10, double& v11) const
 //        -> K[r0][c], K[r0][c+1], K[r1][c], K[r1][c+1]   (lower triangle / rectangular rows; c even)
 //   double rhs(int which, int r) const
-template <class Gen>
+template <class Gen, int TEAM = 0, bool SNAP = false>
 __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const int nrhs, double* scratch,
                            double* zbuf /* [MAXRHS][NCB*NB] solves, then [MAXRHS][NCB*NB] pre-solve w */,
                            FactorSmem& sm, Pipe& pipe, const int snapJ = 1 << 30, double* snap = nullptr, const int snap_n = 0) {
-    // snapshot hook (ITE path): for panels j >= snapJ the value K - sum_{J<snapJ} L L^T (the Schur complement of the
+    // snapshot hook (SNAP = true, ITE path only — the sampler's instantiation carries none of its code, which matters for the
+    // register budget of the k-loops): for panels j >= snapJ the value K - sum_{J<snapJ} L L^T (the Schur complement of the
     // leading snapJ panels, i.e. CovITE + jitter*I) is written to snap[(c-snapJ*NB)*snap_n + (r-snapJ*NB)] (both triangles).
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int npad = NCB * NB;
+    const int trank = TEAM ? (int)cluster_rank() : 0, tsize = TEAM ? (int)cluster_size() : 1;
     if (tid == 0) { sm.info = 0; sm.snap = snap; sm.snapJ = snapJ; sm.snap_n = snap_n; }
     if (tid < NB) { sm.part[0][tid] = 0.0; sm.part[1][tid] = 0.0; sm.part[2][tid] = 0.0; sm.part[3][tid] = 0.0; }
     __syncthreads();
@@ -285,56 +308,63 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                 bulk_g2s(sm.stage + st * STAGE_D + 2 * SLAB_D, scratch + row_off(j) + (size_t)t * SLAB_D, SLAB_D * 8, &sm.full[st]);
             };
             for (int t = 0; t < PF && t < T; t++) produce(t);
-            const bool in_tail = (j >= snapJ);
-            const bool do_snap = in_tail && (snap != nullptr);
+            const bool in_tail = SNAP && (j >= snapJ);
+            const bool do_snap = in_tail && (snap != nullptr) && (trank == 0);
             const int Tsnap = in_tail ? snapJ * NSLAB : T;
-            for (int t = 0; t <= T; t++) {
-                if (in_tail && t == Tsnap) { wsnap[0] = wsum[0]; wsnap[1] = wsum[1]; }
-                if (do_snap && t == Tsnap) {
-                    // Schur complement of the leading snapJ panels for this diagonal tile (lower tiles; mirrored)
-                    const int r = j * NB + warp * 8 + g;
+            auto kloop = [&](const int tb, const int te) {
+                for (int t = tb; t < te; t++) {
+                    if (t + PF < T) produce(t + PF);
+                    const uint32_t gi = pipe.consumed++;
+                    const int st = gi % STAGES;
+                    mbar_wait(&sm.full[st], (gi / STAGES) & 1);
+                    const double* sB = sm.stage + st * STAGE_D + 2 * SLAB_D;
 #pragma unroll
-                    for (int ni = 0; ni < 8; ni++) {
-                        if (ni <= warp) {
-                            const int c = j * NB + ni * 8 + 2 * q;
-                            double v00, v01, v10, v11;
-                            gen.quad(r, r, c, v00, v01, v10, v11);
-                            const int ri = r - snapJ * NB, ci = c - snapJ * NB;
-                            if (ri < snap_n) {
-                                if (ci < snap_n) { snap[(size_t)ci * snap_n + ri] = v00 - acc[ni][0]; snap[(size_t)ri * snap_n + ci] = v00 - acc[ni][0]; }
-                                if (ci + 1 < snap_n) { snap[(size_t)(ci + 1) * snap_n + ri] = v01 - acc[ni][1]; snap[(size_t)ri * snap_n + ci + 1] = v01 - acc[ni][1]; }
+                    for (int k4 = 0; k4 < K4S; k4++) {
+                        const double a = sB[(warp * K4S + k4) * 32 + lane];
+#pragma unroll
+                        for (int ni = 0; ni < 8; ni++) {
+                            if (ni <= warp) {
+                                const double b = sB[(ni * K4S + k4) * 32 + lane];
+                                dmma(acc[ni], a, b);
                             }
                         }
                     }
-                }
-                if (t == T) break;
-                if (t + PF < T) produce(t + PF);
-                const uint32_t gi = pipe.consumed++;
-                const int st = gi % STAGES;
-                mbar_wait(&sm.full[st], (gi / STAGES) & 1);
-                const double* sB = sm.stage + st * STAGE_D + 2 * SLAB_D;
+                    if (nrhs > 0) {
+                        // row wr of the diagonal block row, k columns kq, kq+4, ... of the slab (one double per 8x4 atom row)
 #pragma unroll
-                for (int k4 = 0; k4 < K4S; k4++) {
-                    const double a = sB[(warp * K4S + k4) * 32 + lane];
-#pragma unroll
-                    for (int ni = 0; ni < 8; ni++) {
-                        if (ni <= warp) {
-                            const double b = sB[(ni * K4S + k4) * 32 + lane];
-                            dmma(acc[ni], a, b);
+                        for (int kk = 0; kk < KB / 4; kk++) {
+                            const int kc = kq + 4 * kk;    // column inside the slab
+                            const double l = sB[(wr >> 3) * (K4S * 32) + (kc >> 2) * 32 + (wr & 7) * 4 + (kc & 3)];
+                            for (int rh = 0; rh < nrhs; rh++) wsum[rh] = fma(l, zbuf[(size_t)rh * npad + t * KB + kc], wsum[rh]);
                         }
                     }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.empty[st]);
                 }
-                if (nrhs > 0) {
-                    // row wr of the diagonal block row, k columns kq, kq+4, ... of the slab (one double per 8x4 atom row)
+            };
+            kloop(0, Tsnap);
+            if constexpr (SNAP) {
+                if (in_tail) {
+                    wsnap[0] = wsum[0]; wsnap[1] = wsum[1];
+                    if (do_snap) {
+                        // Schur complement of the leading snapJ panels for this diagonal tile (lower tiles; mirrored)
+                        const int r = j * NB + warp * 8 + g;
 #pragma unroll
-                    for (int kk = 0; kk < KB / 4; kk++) {
-                        const int kc = kq + 4 * kk;    // column inside the slab
-                        const double l = sB[(wr >> 3) * (K4S * 32) + (kc >> 2) * 32 + (wr & 7) * 4 + (kc & 3)];
-                        for (int rh = 0; rh < nrhs; rh++) wsum[rh] = fma(l, zbuf[(size_t)rh * npad + t * KB + kc], wsum[rh]);
+                        for (int ni = 0; ni < 8; ni++) {
+                            if (ni <= warp) {
+                                const int c = j * NB + ni * 8 + 2 * q;
+                                double v00, v01, v10, v11;
+                                gen.quad(r, r, c, v00, v01, v10, v11);
+                                const int ri = r - snapJ * NB, ci = c - snapJ * NB;
+                                if (ri < snap_n) {
+                                    if (ci < snap_n) { snap[(size_t)ci * snap_n + ri] = v00 - acc[ni][0]; snap[(size_t)ri * snap_n + ci] = v00 - acc[ni][0]; }
+                                    if (ci + 1 < snap_n) { snap[(size_t)(ci + 1) * snap_n + ri] = v01 - acc[ni][1]; snap[(size_t)ri * snap_n + ci + 1] = v01 - acc[ni][1]; }
+                                }
+                            }
+                        }
                     }
+                    kloop(Tsnap, T);
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.empty[st]);
             }
             __syncthreads();  // every warp is done with the stage buffers -> P2 may alias them
             double* Cs = sm.stage;
@@ -376,9 +406,11 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
             // store L_jj (lower, zeros above), log-diagonal, z_j = Linv w_j
             {
                 double* dst = scratch + block_off(j, j, NRB);
-                for (int idx = tid; idx < BLOCK_D; idx += FTHREADS) {
-                    const int r = idx >> 6, c = idx & 63;
-                    dst[elem_off(r, c)] = (c <= r) ? Cs[r * CS_LD + c] : 0.0;
+                if (trank == 0) {
+                    for (int idx = tid; idx < BLOCK_D; idx += FTHREADS) {
+                        const int r = idx >> 6, c = idx & 63;
+                        dst[elem_off(r, c)] = (c <= r) ? Cs[r * CS_LD + c] : 0.0;
+                    }
                 }
                 if (tid < NB) sm.part[0][tid] += log(Cs[tid * CS_LD + tid]);
                 if (tid < NB * nrhs) {
@@ -406,7 +438,15 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
         // =================================================================== row tiles below the diagonal
         // Blocks j+1.. are processed two at a time (128-row tiles, warp w owns rows 16w..16w+15); an odd leftover block is
         // processed as a 64-row tile (warp w owns rows 8w..8w+7) so that it costs half a tile of tensor time, not a full one.
-        const int nblk = NRB - j - 1;
+        // team mode: the nblk blocks below the diagonal are dealt out in contiguous runs, the ranks that get one block more
+        // rotate with the panel index
+        int nblk = NRB - j - 1, blk0 = j + 1;
+        if constexpr (TEAM != 0) {
+            const int er = (trank + j) % tsize, per = nblk / tsize, rem = nblk - per * tsize;
+            blk0 += er * per + min(er, rem);
+            nblk = per + (er < rem ? 1 : 0);
+        }
+        const int blk_end = blk0 + nblk;
         const int ntile = (nblk + 1) >> 1;
         const int F = ntile * T;
         // producer position (tile, slab) advances with every call; all threads keep it in step, the elected lane issues
@@ -417,8 +457,8 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
             const int tile = ptile, t = pt;
             if (++pt == T) { pt = 0; ptile++; }
             if (lane != 0 || warp != (int)(gi & (FWARPS - 1))) return;
-            const int I0 = j + 1 + 2 * tile;
-            const bool two = (I0 + 1 < NRB);
+            const int I0 = blk0 + 2 * tile;
+            const bool two = (I0 + 1 < blk_end);
             const int st = gi % STAGES;
             if (gi >= STAGES) mbar_wait(&sm.empty[st], ((gi / STAGES) - 1) & 1);
             mbar_expect_tx(&sm.full[st], (two ? 3 : 2) * SLAB_D * 8);
@@ -430,7 +470,7 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
         };
         for (int f = 0; f < PF && f < F; f++) produce();
         // slab index at which the Schur-complement snapshot is taken, or -1 (parameters live in shared memory)
-        const int Tsnap = (snap != nullptr && j >= snapJ) ? snapJ * NSLAB : -1;
+        const int Tsnap = (SNAP && snap != nullptr && j >= snapJ) ? snapJ * NSLAB : -1;
         // MI = 2: 128-row tile (blocks I0, I0+1); MI = 1: 64-row tile (block I0 only)
         auto run_tile = [&](auto mi_tag, const int I0) {
             constexpr int MI = decltype(mi_tag)::value;
@@ -443,8 +483,36 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
 #pragma unroll
                 for (int ni = 0; ni < 8; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
             const int r0 = I * NB + r8base * 8 + g;
-            for (int t = 0; t <= T; t++) {
-                if (t == Tsnap) {
+            auto kloop = [&](const int tb, const int te) {
+                for (int t = tb; t < te; t++) {
+                    if (prem > 0) produce();
+                    const uint32_t gi = pipe.consumed++;
+                    const int st = gi % STAGES;
+                    mbar_wait(&sm.full[st], (gi / STAGES) & 1);
+                    {
+                        const double* sA = sm.stage + st * STAGE_D + half * SLAB_D + r8base * (K4S * 32);
+                        const double* sB = sm.stage + st * STAGE_D + 2 * SLAB_D;
+#pragma unroll
+                        for (int k4 = 0; k4 < K4S; k4++) {
+                            double a[MI];
+#pragma unroll
+                            for (int mi = 0; mi < MI; mi++) a[mi] = sA[mi * (K4S * 32) + k4 * 32 + lane];
+#pragma unroll
+                            for (int ni = 0; ni < 8; ni++) {
+                                const double b = sB[(ni * K4S + k4) * 32 + lane];
+#pragma unroll
+                                for (int mi = 0; mi < MI; mi++) dmma(acc[mi][ni], a[mi], b);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.empty[st]);
+                }
+            };
+            if constexpr (SNAP) {
+                const int Ts = (Tsnap >= 0) ? Tsnap : T;
+                kloop(0, Ts);
+                if (Tsnap >= 0) {
                     double* snap = sm.snap;
                     const int snapJ = sm.snapJ, snap_n = sm.snap_n;
 #pragma unroll
@@ -471,33 +539,10 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                             }
                         }
                     }
+                    kloop(Ts, T);
                 }
-                if (t == T) break;
-                if (prem > 0) produce();
-                const uint32_t gi = pipe.consumed++;
-                const int st = gi % STAGES;
-                mbar_wait(&sm.full[st], (gi / STAGES) & 1);
-                {
-                    const double* sA = sm.stage + st * STAGE_D + half * SLAB_D + r8base * (K4S * 32);
-                    const double* sB = sm.stage + st * STAGE_D + 2 * SLAB_D;
-#pragma unroll
-                    for (int k4 = 0; k4 < K4S; k4++) {
-                        double a[MI];
-#pragma unroll
-                        for (int mi = 0; mi < MI; mi++) a[mi] = sA[mi * (K4S * 32) + k4 * 32 + lane];
-#pragma unroll
-                        for (int ni = 0; ni < 8; ni++) {
-                            const double b = sB[(ni * K4S + k4) * 32 + lane];
-#pragma unroll
-                            for (int mi = 0; mi < MI; mi++) dmma(acc[mi][ni], a[mi], b);
-                        }
-                        // keep the scheduler from hoisting the next steps' operand loads: with 64 accumulator registers live,
-                        // deeper load hoisting spills accumulators inside this loop
-                        asm volatile("" ::: "memory");
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.empty[st]);
+            } else {
+                kloop(0, T);
             }
             // C = K - acc
 #pragma unroll
@@ -556,12 +601,11 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
             }
         };
         for (int tile = 0; tile < ntile; tile++) {
-            const int I0 = j + 1 + 2 * tile;
-            if (I0 + 1 < NRB) run_tile(std::integral_constant<int, 2>{}, I0);
+            const int I0 = blk0 + 2 * tile;
+            if (I0 + 1 < blk_end) run_tile(std::integral_constant<int, 2>{}, I0);
             else run_tile(std::integral_constant<int, 1>{}, I0);
         }
-        fence_proxy_async();
-        __syncthreads();
+        team_sync<TEAM>();
     }
     // ---- reductions
     __syncthreads();

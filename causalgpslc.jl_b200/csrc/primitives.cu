@@ -6,7 +6,7 @@
 
 namespace gpslc {
 
-int ensure_workspace(Ctx* ctx, int NRB, int NCB, long long tasks, int* grid_out) {
+int ensure_workspace(Ctx* ctx, int NRB, int NCB, long long tasks, int* grid_out, int team) {
     const size_t need = scratch_doubles(NRB, NCB);
     const size_t needz = (size_t)2 * MAXRHS * NCB * NB;
     if (ctx->slots == 0) {
@@ -14,14 +14,16 @@ int ensure_workspace(Ctx* ctx, int NRB, int NCB, long long tasks, int* grid_out)
         const int per = (e && atoi(e) > 0) ? atoi(e) : 2;
         ctx->slots = per * ctx->num_sms;
     }
-    long long grid = tasks < ctx->slots ? tasks : ctx->slots;
+    // team > 1: one L scratch per team (cluster), one z buffer per CTA; *grid_out is the number of teams
+    const long long max_slots = ctx->slots / team;
+    long long grid = tasks < max_slots ? tasks : max_slots;
     if (grid < 1) grid = 1;
     if ((size_t)grid * need > ctx->scratch_cap_d) {
         // bound the slot count by what fits in HBM (n = 8192 augmented: ~1 GiB per slot)
         size_t free_b = 0, total_b = 0;
         GP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
         const size_t avail = (size_t)(0.8 * (double)(free_b + ctx->scratch_cap_d * sizeof(double)));
-        long long fit = (long long)(avail / ((need + needz) * sizeof(double)));
+        long long fit = (long long)(avail / ((need + needz * team) * sizeof(double)));
         if (fit < 1) return ctx->fail(GPSLC_ERR_CUDA, "not enough device memory for one factor workspace");
         if (grid > fit) grid = fit;
     }
@@ -31,11 +33,11 @@ int ensure_workspace(Ctx* ctx, int NRB, int NCB, long long tasks, int* grid_out)
         GP_CUDA(ctx, cudaMalloc(&ctx->scratch, (size_t)grid * need * sizeof(double)));
         ctx->scratch_cap_d = (size_t)grid * need;
     }
-    if ((size_t)grid * needz > ctx->z_cap_d) {
+    if ((size_t)grid * team * needz > ctx->z_cap_d) {
         if (ctx->zbuf) cudaFree(ctx->zbuf);
         ctx->zbuf = nullptr; ctx->z_cap_d = 0;
-        GP_CUDA(ctx, cudaMalloc(&ctx->zbuf, (size_t)grid * needz * sizeof(double)));
-        ctx->z_cap_d = (size_t)grid * needz;
+        GP_CUDA(ctx, cudaMalloc(&ctx->zbuf, (size_t)grid * team * needz * sizeof(double)));
+        ctx->z_cap_d = (size_t)grid * team * needz;
     }
     ctx->slot_scratch_d = need;
     ctx->slot_z_d = needz;

@@ -247,6 +247,30 @@ def test_ite_sate_vs_reference_algebra(ctx, n, n_obj, nX, nU, with_u):
             assert np.allclose(ss, so["samples"][d, c], rtol=1e-7, atol=1e-12)
 
 
+def test_ite_cluster_teams_match_single_cta(ctx, monkeypatch):
+    """Team mode (one thread-block cluster per augmented Cholesky, csrc/factor.cuh) only re-partitions the row blocks of a
+    panel, so MeanITE, CovITE, info and the draws must be bit-identical to the one-CTA-per-task kernel for every team
+    size; ragged n (not a multiple of 64), more tasks than resident clusters is covered by the R x doT x chain product."""
+    for n, n_obj, nX in ((300, 6, 4), (521, 1, 2)):
+        counts, X, T, Y = od.synthetic(n, n_obj, nX, seed=3)
+        md = od.model_data_from_arrays(counts, X, T, Y, nU=1)
+        smp = np.stack([oi.posterior(md, 2, 1, 1, seed=11, chain=c, observe_x=True)[0] for c in range(2)], axis=1)
+        ret = np.array([0, 1], dtype=np.int32)
+        doTs = (0.2, -0.4, 1.0)
+        outs = {}
+        for team in (1, 2, 4, 8):
+            monkeypatch.setenv("GPSLC_TEAM", str(team))
+            outs[team] = ge.ite(smp, X, T, Y, 1, doTs, ret, 1e-10, 5, seed=2, want_cov=True, ctx=ctx)
+        monkeypatch.delenv("GPSLC_TEAM")
+        ref = outs[1]
+        assert ref["info"].max() == 0
+        M, Cv = oe.ite_distributions(md.spec, smp[:, 1, :], X, T, Y, doTs[2], 1, 1, 1e-10)
+        assert np.max(np.abs(M - ref["mean"][2, 1])) <= 1e-8 * np.max(np.abs(M))
+        for team in (2, 4, 8):
+            for key in ("mean", "cov", "samples", "info"):
+                assert np.array_equal(ref[key], outs[team][key]), (n, team, key)
+
+
 def test_zero_effect_identity_through_c_abi(ctx, kats):
     """doT == T => MeanITE == 0 and CovITE == jitter exactly, for U/X present or absent (test/estimation.jl:6-247)."""
     k = kats["conditionalITE_zero_effect"]

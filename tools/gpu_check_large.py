@@ -7,7 +7,10 @@ import gpslc_b200 as g
 from gpslc_b200 import estimation as ge
 from bench import synthetic
 ctx = g.Context(0)
-for n, n_obj, ndot in ((2048, 32, 8), (4096, 64, 8), (8192, 128, 4)):
+cases = ((1024, 16, 15), (2048, 32, 8), (4096, 64, 8), (8192, 128, 32))
+if len(sys.argv) > 1:
+    cases = [c for c in cases if str(c[0]) in sys.argv[1:]]
+for n, n_obj, ndot in cases:
     counts, X, T, Y = synthetic(n, n_obj, 10)
     nX, nU = 10, 1
     n_params = 6 + 4 * nX + 2 * nU + nU * nX
