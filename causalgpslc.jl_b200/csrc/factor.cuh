@@ -19,6 +19,20 @@
 
 namespace gpslc {
 
+// Development aid (-DGPSLC_PHASE_TIMING, tools/gpu_phase_timing.py): cycles thread 0 of every CTA spends in each phase of
+// factor_run, accumulated in a per-translation-unit device array. Compiles to nothing in the product build.
+#ifdef GPSLC_PHASE_TIMING
+static __device__ unsigned long long g_phase_cycles[16];
+#define GP_PHASE_INIT() long long _pt = clock64()
+#define GP_PHASE_MARK(k) do { if (threadIdx.x == 0) { const long long _n = clock64(); atomicAdd(&g_phase_cycles[k], (unsigned long long)(_n - _pt)); _pt = _n; } } while (0)
+#else
+#define GP_PHASE_INIT() do {} while (0)
+#define GP_PHASE_MARK(k) do {} while (0)
+#endif
+
+#ifndef GPSLC_POTF2_VARIANT
+#define GPSLC_POTF2_VARIANT 3
+#endif
 constexpr int NB = 64;                 // panel width == row-block height
 constexpr int KB = 16;                 // k extent of one pipeline slab
 constexpr int K4S = KB / 4;            // 8x4 operand atoms along k per slab
@@ -31,7 +45,8 @@ constexpr int FWARPS = 8;
 constexpr int FTHREADS = FWARPS * 32;
 constexpr int STAGE_D = 3 * SLAB_D;    // A0 | A1 | B
 constexpr int MAXRHS = 2;
-constexpr int CS_LD = 65;              // P2 workspace leading dimension
+constexpr int CS_LD = 66;              // P2 workspace leading dimension (16-byte aligned rows)
+constexpr int CS_ROWS = 72;            // 64 matrix rows + up to MAXRHS right-hand-side rows + zero padding to a full 8-row tile
 constexpr int LINV_D = 72 * 32;        // atoms (n8, k4) with k4 <= 2*n8+1, row n8 starts at atom n8*(n8+1)
 constexpr int CF_DIMS = 24;            // feature dimensions staged per panel (more dimensions fall back to global loads)
 
@@ -134,137 +149,199 @@ __device__ inline void factor_smem_init(FactorSmem& sm) {
 }
 
 // ---------------------------------------------------------------------------------------------- P2
-// Factor the 64x64 block held in Cs (row-major, CS_LD, lower triangle valid), leave L in Cs, L^-1 in sm.linv.
-// ws = workspace after Cs. Returns via sm.info (first bad pivot, 1-based global column) if any.
-__device__ inline void p2_factor_diag(FactorSmem& sm, double* Cs, double* ws, int col0) {
+// Factor the 64x64 diagonal block held in Cs (row-major, CS_LD; the lower 8x8 tiles incl. full diagonal tiles are valid) and
+// apply the same elimination to the right-hand-side rows 64..64+nrhs-1 of Cs (rows up to 71 are zero padding): afterwards
+// Cs holds L_jj (lower triangle) and row 64+i holds z_i = L_jj^-1 w_i — the forward solve falls out of the factorisation
+// of the bordered matrix. sm.linv receives what the row-tile epilogue needs, in B-fragment atoms: the inverses D_b of the
+// eight 8x8 diagonal blocks of L_jj on the block diagonal, and MINUS the sub-diagonal part of L_jj elsewhere.
+//
+// Right-looking over 8-column blocks; per block: 8x8 Cholesky + inverse by warp 0 in registers (the only serial part),
+// then X = A21 D^T and the trailing update A22 -= X X^T as 8x8x4 DMMAs spread over all warps. Everything that is not the
+// 64-pivot chain is tensor work on purpose: while the sibling CTA streams DMMAs, the serial warp issues roughly one
+// instruction per 7 cycles (measured), so this phase is paid for per instruction.
+// Returns via sm.info the first non-positive pivot (1-based global column), if any.
+__device__ __forceinline__ double neg_bits(double x) { return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x)); }
+
+__device__ inline void p2_factor_diag(FactorSmem& sm, double* Cs, int col0) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double* li16 = ws;            // [4][16][17]  inverse of the 16x16 diagonal sub-blocks, li16[b][i][c] = X[i][c]
-    double* Ts = ws + 4 * 16 * 17; // [3][16][17]
+    const int g = lane >> 2, q = lane & 3;
     const unsigned FULL = 0xffffffffu;
-    for (int jb = 0; jb < 4; jb++) {
-        const int c0 = jb * 16;
-        if (warp == 0) {
-            const int r = lane & 15;
-            double a[16];
+    // warp index through a shuffle: tells the compiler the value is warp-uniform, so the shuffles inside `if (warp_u == 0)` are
+    // plain SHFLs instead of WARPSYNC.COLLECTIVE sequences
+    const int warp_u = __shfl_sync(FULL, warp, 0);
+    GP_PHASE_INIT();
+    for (int kb = 0; kb < 8; kb++) {
+        const int c0 = kb * 8;
+        if (warp_u == 0) {
+            // lane r (= lane & 7) holds row r of the 8x8 block; afterwards column r of its inverse
+            const int r = lane & 7;
+            double a[8];
 #pragma unroll
-            for (int k = 0; k < 16; k++) a[k] = (k <= r) ? Cs[(c0 + r) * CS_LD + c0 + k] : 0.0;
+            for (int k = 0; k < 8; k++) a[k] = (k <= r) ? Cs[(c0 + r) * CS_LD + c0 + k] : 0.0;
             double rinv_r = 0.0;
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
+            for (int k = 0; k < 8; k++) {
                 double akk = __shfl_sync(FULL, a[k], k);
                 if (!(akk > 0.0)) {
                     if (lane == 0 && sm.info == 0) sm.info = col0 + c0 + k + 1;
                     akk = 1.0;
                 }
-                double ri = rsqrt(akk);
-                double lk = a[k] * ri;
+                const double ri = rsqrt(akk);
+                const double lk = a[k] * ri;
                 a[k] = lk;
                 if (r == k) rinv_r = ri;
 #pragma unroll
-                for (int j = k + 1; j < 16; j++) {
-                    double ljk = __shfl_sync(FULL, lk, j);
+                for (int j = k + 1; j < 8; j++) {
+                    const double ljk = __shfl_sync(FULL, lk, j);
                     a[j] = fma(-lk, ljk, a[j]);
                 }
             }
-            // inverse, lane c (= r) owns column c of X = L16^-1
-            double x[16];
+            double x[8];
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                double rii = __shfl_sync(FULL, rinv_r, i);
+            for (int i = 0; i < 8; i++) {
+                const double rii = __shfl_sync(FULL, rinv_r, i);
                 double s = 0.0;
 #pragma unroll
                 for (int k = 0; k < i; k++) {
-                    double lik = __shfl_sync(FULL, a[k], i);
+                    const double lik = __shfl_sync(FULL, a[k], i);
                     s = fma(lik, x[k], s);
                 }
                 x[i] = (i == r) ? rii : ((i > r) ? -s * rii : 0.0);
             }
-            if (lane < 16) {
+            if (lane < 8) {
+                // x[i] = D[i][r]: atom (ni = kb, kc = 2 kb + r/4), element (i, r%4); zeros above the diagonal are written too
+                double* at = sm.linv + (kb * (kb + 1) + 2 * kb + (r >> 2)) * 32 + (r & 3);
 #pragma unroll
-                for (int k = 0; k < 16; k++) {
+                for (int k = 0; k < 8; k++) {
                     if (k <= r) Cs[(c0 + r) * CS_LD + c0 + k] = a[k];
-                    li16[(jb * 16 + k) * 17 + r] = x[k];
+                    at[k * 4] = x[k];
                 }
             }
         }
         __syncthreads();
-        const int R = NB - c0 - 16;   // rows below the sub-block
-        if (R > 0) {
-            // TRSM: X[row][col] = sum_{k<=col} A[row][k] * Linv16[col][k]
-            if (tid < R * 4) {
-                const int row = c0 + 16 + (tid >> 2), cq = tid & 3;
-                double arow[16];
-#pragma unroll
-                for (int k = 0; k < 16; k++) arow[k] = Cs[row * CS_LD + c0 + k];
-                __syncwarp();
-                double o[4];
-#pragma unroll
-                for (int cc = 0; cc < 4; cc++) {
-                    const int col = cq * 4 + cc;
-                    double s = 0.0;
-#pragma unroll
-                    for (int k = 0; k < 16; k++)
-                        if (k <= col) s = fma(arow[k], li16[(jb * 16 + col) * 17 + k], s);
-                    o[cc] = s;
-                }
-#pragma unroll
-                for (int cc = 0; cc < 4; cc++) Cs[row * CS_LD + c0 + cq * 4 + cc] = o[cc];
+        GP_PHASE_MARK(8);
+        // X = A21 D^T for the row tiles below (tile 8 = right-hand-side rows); the result replaces A21 and, negated, fills the
+        // sub-diagonal atoms of sm.linv
+        {
+            const int ri = kb + 1 + warp;
+            if (ri <= 8) {
+                double acc[2] = {0.0, 0.0};
+                const double* arow = Cs + (ri * 8 + g) * CS_LD + c0 + q;
+                const double* bat = sm.linv + (kb * (kb + 1) + 2 * kb) * 32 + lane;
+                const double a0 = arow[0], a1 = arow[4];
+                dmma(acc, a0, bat[0]);
+                dmma(acc, a1, bat[32]);
+                __syncwarp();   // every lane has read its A fragments before the tile is overwritten
+                *reinterpret_cast<double2*>(Cs + (ri * 8 + g) * CS_LD + c0 + 2 * q) = make_double2(acc[0], acc[1]);
+                if (ri < 8)
+                    *reinterpret_cast<double2*>(sm.linv + (ri * (ri + 1) + 2 * kb + (q >> 1)) * 32 + g * 4 + ((2 * q) & 3)) =
+                        make_double2(neg_bits(acc[0]), neg_bits(acc[1]));
             }
-            __syncthreads();
-            // SYRK on the trailing part
-            const int base = c0 + 16;
-            for (int idx = tid; idx < R * R; idx += FTHREADS) {
-                const int rr = idx / R, cc = idx - rr * R;
-                if (cc <= rr) {
-                    const double* pr = Cs + (base + rr) * CS_LD + c0;
-                    const double* pc = Cs + (base + cc) * CS_LD + c0;
-                    double s = 0.0;
-#pragma unroll
-                    for (int k = 0; k < 16; k++) s = fma(pr[k], pc[k], s);
-                    Cs[(base + rr) * CS_LD + base + cc] -= s;
-                }
-            }
-            __syncthreads();
-        }
-    }
-    // ---- full inverse into sm.linv (atom layout). Diagonal 16-blocks first (with explicit zeros above the diagonal).
-    for (int idx = tid; idx < 4 * 256; idx += FTHREADS) {
-        const int b = idx >> 8, i = (idx >> 4) & 15, c = idx & 15;
-        if (linv_has(b * 16 + i, b * 16 + c)) sm.linv[linv_off(b * 16 + i, b * 16 + c)] = li16[(b * 16 + i) * 17 + c];
-    }
-    __syncthreads();
-    for (int d = 1; d < 4; d++) {
-        const int nblk = 4 - d;
-        // T_ij = sum_{k=j}^{i-1} L_ik X_kj
-        for (int idx = tid; idx < nblk * 256; idx += FTHREADS) {
-            const int bi = idx >> 8, a = (idx >> 4) & 15, b = idx & 15;
-            const int i = d + bi, j = bi;
-            double s = 0.0;
-            for (int k = j; k < i; k++) {
-#pragma unroll
-                for (int m = 0; m < 16; m++)
-                    if (k > j || m >= b)   // X_jj is lower triangular (entries above its diagonal are not stored)
-                        s = fma(Cs[(16 * i + a) * CS_LD + 16 * k + m], sm.linv[linv_off(16 * k + m, 16 * j + b)], s);
-            }
-            Ts[(bi * 16 + a) * 17 + b] = s;
         }
         __syncthreads();
-        // X_ij = -X_ii T_ij
-        for (int idx = tid; idx < nblk * 256; idx += FTHREADS) {
-            const int bi = idx >> 8, a = (idx >> 4) & 15, b = idx & 15;
-            const int i = d + bi, j = bi;
-            double s = 0.0;
-#pragma unroll
-            for (int m = 0; m < 16; m++)
-                if (m <= a) s = fma(li16[(i * 16 + a) * 17 + m], Ts[(bi * 16 + m) * 17 + b], s);
-            sm.linv[linv_off(16 * i + a, 16 * j + b)] = -s;
+        GP_PHASE_MARK(9);
+        // trailing update: tile (ri, ci) -= X_ri X_ci^T for kb < ci <= min(ri, 7), ri <= 8; tiles dealt round-robin to the warps
+        {
+            int idx = warp;
+            for (int ri = kb + 1; ri <= 8; ri++) {
+                const int width = min(ri, 7) - kb;
+                while (idx < width) {
+                    const int ci = kb + 1 + idx;
+                    const double* arow = Cs + (ri * 8 + g) * CS_LD + c0 + q;
+                    const double* brow = Cs + (ci * 8 + g) * CS_LD + c0 + q;
+                    double2* cp = reinterpret_cast<double2*>(Cs + (ri * 8 + g) * CS_LD + ci * 8 + 2 * q);
+                    const double2 cv = *cp;
+                    double acc[2] = {cv.x, cv.y};
+                    dmma(acc, neg_bits(arow[0]), brow[0]);
+                    dmma(acc, neg_bits(arow[4]), brow[4]);
+                    *cp = make_double2(acc[0], acc[1]);
+                    idx += FWARPS;
+                }
+                idx -= width;
+            }
         }
         __syncthreads();
+        GP_PHASE_MARK(10);
     }
 }
 
 // ---------------------------------------------------------------------------------------------- main routine
 struct Pipe { uint32_t produced; uint32_t consumed; };
+
+// Row-tile operand producer: slab t of tile `tile` of panel j (A rows of blocks I0 [, I0+1] and the B rows of block j) goes
+// into pipeline slot gi. Called by one elected lane.
+__device__ __forceinline__ void issue_row_slab(FactorSmem& sm, const double* scratch, int j, int T, int blk0, int blk_end, int tile,
+                                               int t, uint32_t gi) {
+    const int I0 = blk0 + 2 * tile;
+    const bool two = (I0 + 1 < blk_end);
+    const int st = gi % STAGES;
+    if (gi >= STAGES) mbar_wait(&sm.empty[st], ((gi / STAGES) - 1) & 1);
+    mbar_expect_tx(&sm.full[st], (two ? 3 : 2) * SLAB_D * 8);
+    double* dst = sm.stage + st * STAGE_D;
+    const size_t so = (size_t)t * SLAB_D;
+    bulk_g2s(dst, scratch + row_off(I0) + so, SLAB_D * 8, &sm.full[st]);
+    if (two) bulk_g2s(dst + SLAB_D, scratch + row_off(I0 + 1) + so, SLAB_D * 8, &sm.full[st]);
+    bulk_g2s(dst + 2 * SLAB_D, scratch + row_off(j) + so, SLAB_D * 8, &sm.full[st]);
+}
+
+// The k-loop of one row tile, slabs [tb, te): acc -= nothing yet, acc += A_slab x B_slab^T over the slabs. It is a separate
+// NON-INLINED function on purpose: inlined into factor_run, the 64 accumulator registers plus the operand fragments
+// compete with everything factor_run keeps live across the loop (generator, panel and tile bookkeeping), and ptxas
+// spilled accumulators on every slab iteration; as a call, the caller's state is saved once per tile and the loop runs
+// spill-free. acc travels through local memory (accio, MI*16 doubles): zero-initialised when tb == 0.
+// gi0 = pipeline sequence number of slab tb; the slab PF ahead in the panel's (tile, t) order is issued as it goes.
+template <int MI>
+__device__ __noinline__ void row_tile_kloop(double* __restrict__ accio, const double* __restrict__ scratch, const int j, const int T,
+                                            const int blk0, const int blk_end, const int tile, const int F, const int tb, const int te,
+                                            const uint32_t gi0) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FactorSmem& sm = *reinterpret_cast<FactorSmem*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int half = (MI == 2) ? (warp >> 2) : 0;
+    const int r8base = (MI == 2) ? (warp & 3) * 2 : warp;
+    double acc[MI][8][2];
+#pragma unroll
+    for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 8; ni++) {
+            acc[mi][ni][0] = (tb == 0) ? 0.0 : accio[(mi * 8 + ni) * 2];
+            acc[mi][ni][1] = (tb == 0) ? 0.0 : accio[(mi * 8 + ni) * 2 + 1];
+        }
+    uint32_t gi = gi0;
+    const int fbase = tile * T + PF;
+    for (int t = tb; t < te; t++, gi++) {
+        if (fbase + t < F && lane == 0 && warp == (int)((gi + PF) & (FWARPS - 1))) {
+            int pt = t + PF, ptile = tile;
+            if (pt >= T) { pt -= T; ptile++; }
+            issue_row_slab(sm, scratch, j, T, blk0, blk_end, ptile, pt, gi + PF);
+        }
+        const int st = gi % STAGES;
+        mbar_wait(&sm.full[st], (gi / STAGES) & 1);
+        const double* sA = sm.stage + st * STAGE_D + half * SLAB_D + r8base * (K4S * 32);
+        const double* sB = sm.stage + st * STAGE_D + 2 * SLAB_D;
+#pragma unroll
+        for (int k4 = 0; k4 < K4S; k4++) {
+            double a[MI];
+#pragma unroll
+            for (int mi = 0; mi < MI; mi++) a[mi] = sA[mi * (K4S * 32) + k4 * 32 + lane];
+#pragma unroll
+            for (int ni = 0; ni < 8; ni++) {
+                const double b = sB[(ni * K4S + k4) * 32 + lane];
+#pragma unroll
+                for (int mi = 0; mi < MI; mi++) dmma(acc[mi][ni], a[mi], b);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[st]);
+    }
+#pragma unroll
+    for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 8; ni++) {
+            accio[(mi * 8 + ni) * 2] = acc[mi][ni][0];
+            accio[(mi * 8 + ni) * 2 + 1] = acc[mi][ni][1];
+        }
+}
 
 // Gen concept:
 //   void quad(int r0, int r1, int c, double& v00, double& v01, double& v10, double& v11) const
@@ -285,6 +362,7 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
     if (tid < NB) { sm.part[0][tid] = 0.0; sm.part[1][tid] = 0.0; sm.part[2][tid] = 0.0; sm.part[3][tid] = 0.0; }
     __syncthreads();
 
+    GP_PHASE_INIT();
     for (int j = 0; j < NCB; j++) {
         const int T = j * NSLAB;  // slabs in the k-loop of this panel
         gen.stage_cols(j * NB, sm.colfeat);
@@ -367,8 +445,8 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                 }
             }
             __syncthreads();  // every warp is done with the stage buffers -> P2 may alias them
-            double* Cs = sm.stage;
-            double* ws = sm.stage + NB * CS_LD;
+            GP_PHASE_MARK(0);
+            double* Cs = sm.stage;   // [CS_ROWS][CS_LD]
             // C_jj = K_jj - acc  (lower tiles only)
             {
                 const int r = j * NB + warp * 8 + g;
@@ -393,7 +471,7 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                 s += __shfl_xor_sync(0xffffffffu, s, 1);
                 s += __shfl_xor_sync(0xffffffffu, s, 2);
                 const double yv = gen.rhs(rh, j * NB + wr);
-                if (kq == 0) sm.wvec[rh][wr] = yv - s;
+                if (kq == 0) { sm.wvec[rh][wr] = yv - s; Cs[(NB + rh) * CS_LD + wr] = yv - s; }
                 if (in_tail) {
                     double s2 = wsnap[rh];
                     s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
@@ -401,9 +479,13 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                     if (kq == 0) zbuf[(size_t)(MAXRHS + rh) * npad + j * NB + wr] = yv - s2;
                 }
             }
+            for (int idx = tid; idx < (CS_ROWS - NB - nrhs) * NB; idx += FTHREADS)   // zero padding below the right-hand sides
+                Cs[(NB + nrhs + (idx >> 6)) * CS_LD + (idx & 63)] = 0.0;
             __syncthreads();
-            p2_factor_diag(sm, Cs, ws, j * NB);
-            // store L_jj (lower, zeros above), log-diagonal, z_j = Linv w_j
+            GP_PHASE_MARK(1);
+            p2_factor_diag(sm, Cs, j * NB);
+            GP_PHASE_MARK(5);
+            // store L_jj (lower, zeros above), log-diagonal, z_j = L_jj^-1 w_j (rows 64.. of the bordered factorisation)
             {
                 double* dst = scratch + block_off(j, j, NRB);
                 if (trank == 0) {
@@ -415,9 +497,7 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                 if (tid < NB) sm.part[0][tid] += log(Cs[tid * CS_LD + tid]);
                 if (tid < NB * nrhs) {
                     const int rh = tid >> 6, r = tid & 63;
-                    double s = 0.0;
-                    for (int c = 0; c <= r; c++) s = fma(sm.linv[linv_off(r, c)], sm.wvec[rh][c], s);
-                    zbuf[(size_t)rh * npad + j * NB + r] = s;
+                    zbuf[(size_t)rh * npad + j * NB + r] = Cs[(NB + rh) * CS_LD + r];
                     if (!in_tail) zbuf[(size_t)(MAXRHS + rh) * npad + j * NB + r] = sm.wvec[rh][r];
                 }
             }
@@ -434,6 +514,7 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
             }
             fence_proxy_async();   // generic-proxy writes (smem workspace, global L_jj) before later async-proxy copies
             __syncthreads();
+            GP_PHASE_MARK(6);
         }
         // =================================================================== row tiles below the diagonal
         // Blocks j+1.. are processed two at a time (128-row tiles, warp w owns rows 16w..16w+15); an odd leftover block is
@@ -449,70 +530,38 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
         const int blk_end = blk0 + nblk;
         const int ntile = (nblk + 1) >> 1;
         const int F = ntile * T;
-        // producer position (tile, slab) advances with every call; all threads keep it in step, the elected lane issues
-        int ptile = 0, pt = 0, prem = F;
-        auto produce = [&]() {
-            prem--;
-            const uint32_t gi = pipe.produced++;
-            const int tile = ptile, t = pt;
-            if (++pt == T) { pt = 0; ptile++; }
-            if (lane != 0 || warp != (int)(gi & (FWARPS - 1))) return;
-            const int I0 = blk0 + 2 * tile;
-            const bool two = (I0 + 1 < blk_end);
-            const int st = gi % STAGES;
-            if (gi >= STAGES) mbar_wait(&sm.empty[st], ((gi / STAGES) - 1) & 1);
-            mbar_expect_tx(&sm.full[st], (two ? 3 : 2) * SLAB_D * 8);
-            double* dst = sm.stage + st * STAGE_D;
-            const size_t so = (size_t)t * SLAB_D;
-            bulk_g2s(dst, scratch + row_off(I0) + so, SLAB_D * 8, &sm.full[st]);
-            if (two) bulk_g2s(dst + SLAB_D, scratch + row_off(I0 + 1) + so, SLAB_D * 8, &sm.full[st]);
-            bulk_g2s(dst + 2 * SLAB_D, scratch + row_off(j) + so, SLAB_D * 8, &sm.full[st]);
-        };
-        for (int f = 0; f < PF && f < F; f++) produce();
+        // prologue of the operand pipeline: the first PF slabs of the panel (the k-loops issue the rest as they go)
+        for (int f = 0; f < PF && f < F; f++) {
+            const uint32_t gi = pipe.consumed + f;
+            if (lane == 0 && warp == (int)(gi & (FWARPS - 1))) issue_row_slab(sm, scratch, j, T, blk0, blk_end, f / T, f % T, gi);
+        }
         // slab index at which the Schur-complement snapshot is taken, or -1 (parameters live in shared memory)
         const int Tsnap = (SNAP && snap != nullptr && j >= snapJ) ? snapJ * NSLAB : -1;
         // MI = 2: 128-row tile (blocks I0, I0+1); MI = 1: 64-row tile (block I0 only)
-        auto run_tile = [&](auto mi_tag, const int I0) {
+        auto run_tile = [&](auto mi_tag, const int tile) {
             constexpr int MI = decltype(mi_tag)::value;
+            const int I0 = blk0 + 2 * tile;
             const int half = (MI == 2) ? (warp >> 2) : 0;
             const int I = I0 + half;                                   // block this warp works on
             const int r8base = (MI == 2) ? (warp & 3) * 2 : warp;      // first 8-row group of this warp inside block I
+            double accm[MI * 16];                                      // local memory: filled by the non-inlined k-loop
             double acc[MI][8][2];
-#pragma unroll
-            for (int mi = 0; mi < MI; mi++)
-#pragma unroll
-                for (int ni = 0; ni < 8; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
             const int r0 = I * NB + r8base * 8 + g;
             auto kloop = [&](const int tb, const int te) {
-                for (int t = tb; t < te; t++) {
-                    if (prem > 0) produce();
-                    const uint32_t gi = pipe.consumed++;
-                    const int st = gi % STAGES;
-                    mbar_wait(&sm.full[st], (gi / STAGES) & 1);
-                    {
-                        const double* sA = sm.stage + st * STAGE_D + half * SLAB_D + r8base * (K4S * 32);
-                        const double* sB = sm.stage + st * STAGE_D + 2 * SLAB_D;
+                row_tile_kloop<MI>(accm, scratch, j, T, blk0, blk_end, tile, F, tb, te, pipe.consumed);
+                pipe.consumed += te - tb;
+            };
+            auto fetch_acc = [&]() {
 #pragma unroll
-                        for (int k4 = 0; k4 < K4S; k4++) {
-                            double a[MI];
+                for (int mi = 0; mi < MI; mi++)
 #pragma unroll
-                            for (int mi = 0; mi < MI; mi++) a[mi] = sA[mi * (K4S * 32) + k4 * 32 + lane];
-#pragma unroll
-                            for (int ni = 0; ni < 8; ni++) {
-                                const double b = sB[(ni * K4S + k4) * 32 + lane];
-#pragma unroll
-                                for (int mi = 0; mi < MI; mi++) dmma(acc[mi][ni], a[mi], b);
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&sm.empty[st]);
-                }
+                    for (int ni = 0; ni < 8; ni++) { acc[mi][ni][0] = accm[(mi * 8 + ni) * 2]; acc[mi][ni][1] = accm[(mi * 8 + ni) * 2 + 1]; }
             };
             if constexpr (SNAP) {
                 const int Ts = (Tsnap >= 0) ? Tsnap : T;
                 kloop(0, Ts);
                 if (Tsnap >= 0) {
+                    fetch_acc();
                     double* snap = sm.snap;
                     const int snapJ = sm.snapJ, snap_n = sm.snap_n;
 #pragma unroll
@@ -544,11 +593,16 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
             } else {
                 kloop(0, T);
             }
-            // C = K - acc
+            GP_PHASE_MARK(2);
+            fetch_acc();
+            // C = K - acc. The row index is laundered through an empty asm so that nothing of the covariance generation
+            // (feature loads, address arithmetic) can be scheduled into the k-loop, where every register is needed
+            int r0g = r0;
+            asm volatile("" : "+r"(r0g));
 #pragma unroll
             for (int h4 = 0; h4 < 2; h4++) {
                 double v[2][4][2];
-                gen.template strip<4, MI == 1>(r0, r0 + 8, j * NB + h4 * 32 + 2 * q, v, sm.colfeat, h4 * 32 + 2 * q);
+                gen.template strip<4, MI == 1>(r0g, r0g + 8, j * NB + h4 * 32 + 2 * q, v, sm.colfeat, h4 * 32 + 2 * q);
 #pragma unroll
                 for (int nn = 0; nn < 4; nn++)
 #pragma unroll
@@ -557,55 +611,52 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                         acc[mi][h4 * 4 + nn][1] = v[mi][nn][1] - acc[mi][h4 * 4 + nn][1];
                     }
             }
-            // L_Ij = C Linv^T : out[:, ni] = sum_{kc <= 2ni+1} Afrag(kc) x Linv[ni-tile rows][kc]; A-fragments are rebuilt from the
-            // accumulators with quad shuffles (lane (g,q) needs C[g][4h+q], held by lane (g, 2h + q/2), element q%2)
+            // L_Ij = C L_jj^-T by block forward substitution over the eight 8-column tiles, right-looking:
+            //   X_b = R_b D_b^T   (D_b = inverse of the b-th 8x8 diagonal block; sm.linv atoms (b, 2b), (b, 2b+1))
+            //   R_c -= X_b L_cb^T for c > b   (atoms (c, 2b), (c, 2b+1) hold -L_cb)
+            // so the 64x64 inverse of L_jj is never formed. A-fragments are rebuilt from accumulator-layout values with quad
+            // shuffles (lane (g,q) needs V[g][4h+q], held by lane (g, 2h + q/2), element q%2).
             double* dst = scratch + block_off(I, j, NRB);
+            auto to_afrag = [&](const double (&t)[2], const int hh) {
+                const int src = (lane & ~3) | (2 * hh + (q >> 1));
+                const double v0 = __shfl_sync(0xffffffffu, t[0], src);
+                const double v1 = __shfl_sync(0xffffffffu, t[1], src);
+                return (q & 1) ? v1 : v0;
+            };
 #pragma unroll
-            for (int nig = 0; nig < 8; nig += 4) {
-                double o[MI][4][2];
+            for (int b = 0; b < 8; b++) {
+                const double* datom = sm.linv + (b * (b + 1) + 2 * b) * 32 + lane;
+                double o[MI][2];
 #pragma unroll
-                for (int mi = 0; mi < MI; mi++)
+                for (int mi = 0; mi < MI; mi++) {
+                    o[mi][0] = 0.0; o[mi][1] = 0.0;
+                    const double r0f = to_afrag(acc[mi][b], 0), r1f = to_afrag(acc[mi][b], 1);
+                    dmma(o[mi], r0f, datom[0]);
+                    dmma(o[mi], r1f, datom[32]);
+                    *reinterpret_cast<double2*>(dst + elem_off((r8base + mi) * 8 + g, b * 8 + 2 * q)) = make_double2(o[mi][0], o[mi][1]);
+                }
+                if (b < 7) {
+                    double xf[MI][2];
 #pragma unroll
-                    for (int nn = 0; nn < 4; nn++) { o[mi][nn][0] = 0.0; o[mi][nn][1] = 0.0; }
+                    for (int mi = 0; mi < MI; mi++) { xf[mi][0] = to_afrag(o[mi], 0); xf[mi][1] = to_afrag(o[mi], 1); }
 #pragma unroll
-                for (int kc = 0; kc < 16; kc++) {
-                    if (kc <= 2 * (nig + 3) + 1) {
-                        const int tt = kc >> 1, hh = kc & 1;
-                        const int src = (lane & ~3) | (2 * hh + (q >> 1));
-                        double a[MI];
+                    for (int c = b + 1; c < 8; c++) {
+                        const double* latom = sm.linv + (c * (c + 1) + 2 * b) * 32 + lane;
+                        const double l0 = latom[0], l1 = latom[32];
 #pragma unroll
-                        for (int mi = 0; mi < MI; mi++) {
-                            const double v0 = __shfl_sync(0xffffffffu, acc[mi][tt][0], src);
-                            const double v1 = __shfl_sync(0xffffffffu, acc[mi][tt][1], src);
-                            a[mi] = (q & 1) ? v1 : v0;
-                        }
-#pragma unroll
-                        for (int nn = 0; nn < 4; nn++) {
-                            const int ni = nig + nn;
-                            if (kc <= 2 * ni + 1) {
-                                const double b = sm.linv[(ni * (ni + 1) + kc) * 32 + lane];
-#pragma unroll
-                                for (int mi = 0; mi < MI; mi++) dmma(o[mi][nn], a[mi], b);
-                            }
-                        }
+                        for (int mi = 0; mi < MI; mi++) { dmma(acc[mi][c], xf[mi][0], l0); dmma(acc[mi][c], xf[mi][1], l1); }
                     }
                 }
-#pragma unroll
-                for (int mi = 0; mi < MI; mi++)
-#pragma unroll
-                    for (int nn = 0; nn < 4; nn++) {
-                        const int ni = nig + nn;
-                        double2 v = make_double2(o[mi][nn][0], o[mi][nn][1]);
-                        *reinterpret_cast<double2*>(dst + elem_off((r8base + mi) * 8 + g, ni * 8 + 2 * q)) = v;
-                    }
             }
         };
         for (int tile = 0; tile < ntile; tile++) {
-            const int I0 = blk0 + 2 * tile;
-            if (I0 + 1 < blk_end) run_tile(std::integral_constant<int, 2>{}, I0);
-            else run_tile(std::integral_constant<int, 1>{}, I0);
+            if (blk0 + 2 * tile + 1 < blk_end) run_tile(std::integral_constant<int, 2>{}, tile);
+            else run_tile(std::integral_constant<int, 1>{}, tile);
         }
+        pipe.produced = pipe.consumed;   // everything issued for this panel has been consumed
+        GP_PHASE_MARK(3);
         team_sync<TEAM>();
+        GP_PHASE_MARK(4);
     }
     // ---- reductions
     __syncthreads();

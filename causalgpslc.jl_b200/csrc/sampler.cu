@@ -214,6 +214,9 @@ mh_lanes_kernel(ModelDev m, ChainDev c, const int* lane_order, int outer, int j0
     __shared__ unsigned int job;
     __shared__ double s_new, s_part;
     factor_smem_init(sm);
+#ifdef GPSLC_PHASE_TIMING
+    const long long _k0 = clock64();
+#endif
     Pipe pipe{0, 0};
     const int NCB = ceil_div(m.n, NB);
     double* my_scratch = scratch + (size_t)blockIdx.x * slot_scratch;
@@ -284,7 +287,21 @@ mh_lanes_kernel(ModelDev m, ChainDev c, const int* lane_order, int outer, int j0
             }
         }
     }
+#ifdef GPSLC_PHASE_TIMING
+    if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[7], (unsigned long long)(clock64() - _k0));
+#endif
 }
+
+#ifdef GPSLC_PHASE_TIMING
+}  // namespace gpslc
+extern "C" int gpslc_debug_phase_cycles(unsigned long long* out8, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out8, gpslc::g_phase_cycles, 16 * sizeof(unsigned long long));
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(gpslc::g_phase_cycles, z, sizeof(z)); }
+    return 0;
+}
+namespace gpslc {
+#endif
 
 // ------------------------------------------------------------------------------------------------ ESS over U_k
 constexpr int ESS_MAX_EVALS = 200;

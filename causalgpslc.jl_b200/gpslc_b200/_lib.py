@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libgpslc_b200.so")
+# GPSLC_LIB_SUFFIX selects a development build of the same sources (build.sh), e.g. "_prof" for the phase-timing build
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libgpslc_b200" + os.environ.get("GPSLC_LIB_SUFFIX", "") + ".so")
 
 HOST, DEVICE = 0, 1
 
