@@ -369,9 +369,20 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
         __syncthreads();
         // =================================================================== diagonal tile
         {
-            double acc[8][2];
+            // The 36 lower 8x8 tiles of the diagonal block are dealt 5/4 to the warps (instead of w+1 to warp w): warps p and
+            // p+4 share the row-tile pair (p, 7-p), which has 9 tiles: warp p takes row p and the first 4-p tiles of row 7-p,
+            // warp p+4 the other four. Slot s of a warp is tile (srow[s], scol[s]).
+            constexpr int DSLOTS = 5;
+            const int pw = warp & 3, nslots = (warp < 4) ? 5 : 4;
+            int srow[DSLOTS], scol[DSLOTS];
 #pragma unroll
-            for (int ni = 0; ni < 8; ni++) { acc[ni][0] = 0.0; acc[ni][1] = 0.0; }
+            for (int sl = 0; sl < DSLOTS; sl++) {
+                if (warp < 4) { srow[sl] = (sl <= pw) ? pw : 7 - pw; scol[sl] = (sl <= pw) ? sl : sl - pw - 1; }
+                else { srow[sl] = 7 - pw; scol[sl] = min(4 - pw + sl, 7); }
+            }
+            double acc[DSLOTS][2];
+#pragma unroll
+            for (int sl = 0; sl < DSLOTS; sl++) { acc[sl][0] = 0.0; acc[sl][1] = 0.0; }
             double wsum[MAXRHS] = {0.0, 0.0};
             double wsnap[MAXRHS] = {0.0, 0.0};  // residual after the leading snapJ panels only (ITE: -MeanITE)
             const int wr = tid >> 2, kq = tid & 3;  // RHS update mapping: row wr, k pair kq
@@ -398,12 +409,12 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                     const double* sB = sm.stage + st * STAGE_D + 2 * SLAB_D;
 #pragma unroll
                     for (int k4 = 0; k4 < K4S; k4++) {
-                        const double a = sB[(warp * K4S + k4) * 32 + lane];
 #pragma unroll
-                        for (int ni = 0; ni < 8; ni++) {
-                            if (ni <= warp) {
-                                const double b = sB[(ni * K4S + k4) * 32 + lane];
-                                dmma(acc[ni], a, b);
+                        for (int sl = 0; sl < DSLOTS; sl++) {
+                            if (sl < nslots) {
+                                const double a = sB[(srow[sl] * K4S + k4) * 32 + lane];
+                                const double b = sB[(scol[sl] * K4S + k4) * 32 + lane];
+                                dmma(acc[sl], a, b);
                             }
                         }
                     }
@@ -426,17 +437,17 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                     wsnap[0] = wsum[0]; wsnap[1] = wsum[1];
                     if (do_snap) {
                         // Schur complement of the leading snapJ panels for this diagonal tile (lower tiles; mirrored)
-                        const int r = j * NB + warp * 8 + g;
 #pragma unroll
-                        for (int ni = 0; ni < 8; ni++) {
-                            if (ni <= warp) {
-                                const int c = j * NB + ni * 8 + 2 * q;
+                        for (int sl = 0; sl < DSLOTS; sl++) {
+                            if (sl < nslots) {
+                                const int r = j * NB + srow[sl] * 8 + g;
+                                const int c = j * NB + scol[sl] * 8 + 2 * q;
                                 double v00, v01, v10, v11;
                                 gen.quad(r, r, c, v00, v01, v10, v11);
                                 const int ri = r - snapJ * NB, ci = c - snapJ * NB;
                                 if (ri < snap_n) {
-                                    if (ci < snap_n) { snap[(size_t)ci * snap_n + ri] = v00 - acc[ni][0]; snap[(size_t)ri * snap_n + ci] = v00 - acc[ni][0]; }
-                                    if (ci + 1 < snap_n) { snap[(size_t)(ci + 1) * snap_n + ri] = v01 - acc[ni][1]; snap[(size_t)ri * snap_n + ci + 1] = v01 - acc[ni][1]; }
+                                    if (ci < snap_n) { snap[(size_t)ci * snap_n + ri] = v00 - acc[sl][0]; snap[(size_t)ri * snap_n + ci] = v00 - acc[sl][0]; }
+                                    if (ci + 1 < snap_n) { snap[(size_t)(ci + 1) * snap_n + ri] = v01 - acc[sl][1]; snap[(size_t)ri * snap_n + ci + 1] = v01 - acc[sl][1]; }
                                 }
                             }
                         }
@@ -447,23 +458,14 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
             __syncthreads();  // every warp is done with the stage buffers -> P2 may alias them
             GP_PHASE_MARK(0);
             double* Cs = sm.stage;   // [CS_ROWS][CS_LD]
-            // C_jj = K_jj - acc  (lower tiles only)
-            {
-                const int r = j * NB + warp * 8 + g;
+            // C_jj = K_jj - acc  (lower tiles only; diagonal tiles in full)
 #pragma unroll
-                for (int h4 = 0; h4 < 2; h4++) {
-                    if (h4 * 4 <= warp) {
-                        double v[2][4][2];
-                        gen.template strip<4, true>(r, r, j * NB + h4 * 32 + 2 * q, v, sm.colfeat, h4 * 32 + 2 * q);
-#pragma unroll
-                        for (int nn = 0; nn < 4; nn++) {
-                            const int ni = h4 * 4 + nn;
-                            if (ni <= warp) {
-                                Cs[(warp * 8 + g) * CS_LD + ni * 8 + 2 * q] = v[0][nn][0] - acc[ni][0];
-                                Cs[(warp * 8 + g) * CS_LD + ni * 8 + 2 * q + 1] = v[0][nn][1] - acc[ni][1];
-                            }
-                        }
-                    }
+            for (int sl = 0; sl < DSLOTS; sl++) {
+                if (sl < nslots) {
+                    const int rl = srow[sl] * 8 + g, cl = scol[sl] * 8 + 2 * q;
+                    double v[2][1][2];
+                    gen.template strip<1, true>(j * NB + rl, j * NB + rl, j * NB + cl, v, sm.colfeat, cl);
+                    *reinterpret_cast<double2*>(Cs + rl * CS_LD + cl) = make_double2(v[0][0][0] - acc[sl][0], v[0][0][1] - acc[sl][1]);
                 }
             }
             for (int rh = 0; rh < nrhs; rh++) {
