@@ -40,7 +40,6 @@ constexpr int NSLAB = NB / KB;         // slabs per block
 constexpr int SLAB_D = NB * KB;        // doubles per slab (8 KB)
 constexpr int BLOCK_D = NB * NB;       // doubles per block (32 KB)
 constexpr int STAGES = 3;
-constexpr int PF = 2;                  // prefetch distance (slabs)
 constexpr int FWARPS = 8;
 constexpr int FTHREADS = FWARPS * 32;
 constexpr int STAGE_D = 3 * SLAB_D;    // A0 | A1 | B
@@ -65,7 +64,7 @@ struct __align__(128) FactorSmem {
     double* snap; int snapJ, snap_n;   // snapshot hook parameters
     double red[32];
     unsigned long long full[STAGES];
-    unsigned long long empty[STAGES];
+    unsigned int freed[STAGES];        // warps that have finished with the slab in each stage (the last one refills it)
     FactorOut out;
     int info;
 };
@@ -98,6 +97,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Stage release without an "empty" mbarrier and without a waiting producer: every warp counts itself out of a stage with an
+// acq_rel shared-memory atomic; the warp that arrives last (and only that one) resets the counter and immediately issues the
+// TMA copies that refill the stage, so no consumer warp ever blocks on the slowest one and the prefetch depth is the full ring.
+__device__ __forceinline__ bool stage_release_is_last(unsigned int* cnt) {
+    unsigned int old;
+    asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(cnt)) : "memory");
+    if (old != FWARPS - 1) return false;
+    *reinterpret_cast<volatile unsigned int*>(cnt) = 0;
+    return true;
+}
 
 // Team mode (TEAM = 1): the CTAs of one thread-block cluster factor ONE matrix together (few large matrices, e.g. the
 // n = 8192 counterfactual sweep, where one CTA per matrix would leave most SMs idle). The L scratch in global memory is shared by
@@ -142,7 +151,7 @@ __device__ __forceinline__ bool linv_has(int n, int k) { return (k >> 2) <= 2 * 
 
 __device__ inline void factor_smem_init(FactorSmem& sm) {
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], FWARPS); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(&sm.full[s], 1); sm.freed[s] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -269,13 +278,12 @@ __device__ inline void p2_factor_diag(FactorSmem& sm, double* Cs, int col0) {
 struct Pipe { uint32_t produced; uint32_t consumed; };
 
 // Row-tile operand producer: slab t of tile `tile` of panel j (A rows of blocks I0 [, I0+1] and the B rows of block j) goes
-// into pipeline slot gi. Called by one elected lane.
+// into pipeline slot gi, whose stage must be free. Called by one lane.
 __device__ __forceinline__ void issue_row_slab(FactorSmem& sm, const double* scratch, int j, int T, int blk0, int blk_end, int tile,
                                                int t, uint32_t gi) {
     const int I0 = blk0 + 2 * tile;
     const bool two = (I0 + 1 < blk_end);
     const int st = gi % STAGES;
-    if (gi >= STAGES) mbar_wait(&sm.empty[st], ((gi / STAGES) - 1) & 1);
     mbar_expect_tx(&sm.full[st], (two ? 3 : 2) * SLAB_D * 8);
     double* dst = sm.stage + st * STAGE_D;
     const size_t so = (size_t)t * SLAB_D;
@@ -289,7 +297,8 @@ __device__ __forceinline__ void issue_row_slab(FactorSmem& sm, const double* scr
 // compete with everything factor_run keeps live across the loop (generator, panel and tile bookkeeping), and ptxas
 // spilled accumulators on every slab iteration; as a call, the caller's state is saved once per tile and the loop runs
 // spill-free. acc travels through local memory (accio, MI*16 doubles): zero-initialised when tb == 0.
-// gi0 = pipeline sequence number of slab tb; the slab PF ahead in the panel's (tile, t) order is issued as it goes.
+// gi0 = pipeline sequence number of slab tb; a stage is refilled (slab STAGES ahead in the panel's (tile, t) order) by the
+// last warp that leaves it.
 template <int MI>
 __device__ __noinline__ void row_tile_kloop(double* __restrict__ accio, const double* __restrict__ scratch, const int j, const int T,
                                             const int blk0, const int blk_end, const int tile, const int F, const int tb, const int te,
@@ -308,15 +317,20 @@ __device__ __noinline__ void row_tile_kloop(double* __restrict__ accio, const do
             acc[mi][ni][1] = (tb == 0) ? 0.0 : accio[(mi * 8 + ni) * 2 + 1];
         }
     uint32_t gi = gi0;
-    const int fbase = tile * T + PF;
+#ifdef GPSLC_PHASE_TIMING
+    long long _wait = 0, _prod = 0;
+    const long long _f0 = clock64();
+#endif
+    const int fbase = tile * T + STAGES;
     for (int t = tb; t < te; t++, gi++) {
-        if (fbase + t < F && lane == 0 && warp == (int)((gi + PF) & (FWARPS - 1))) {
-            int pt = t + PF, ptile = tile;
-            if (pt >= T) { pt -= T; ptile++; }
-            issue_row_slab(sm, scratch, j, T, blk0, blk_end, ptile, pt, gi + PF);
-        }
         const int st = gi % STAGES;
+#ifdef GPSLC_PHASE_TIMING
+        const long long _w0 = clock64();
+#endif
         mbar_wait(&sm.full[st], (gi / STAGES) & 1);
+#ifdef GPSLC_PHASE_TIMING
+        _wait += clock64() - _w0;
+#endif
         const double* sA = sm.stage + st * STAGE_D + half * SLAB_D + r8base * (K4S * 32);
         const double* sB = sm.stage + st * STAGE_D + 2 * SLAB_D;
 #pragma unroll
@@ -332,7 +346,18 @@ __device__ __noinline__ void row_tile_kloop(double* __restrict__ accio, const do
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[st]);
+        if (lane == 0 && stage_release_is_last(&sm.freed[st]) && fbase + t < F) {
+            // this warp was the last one out of the stage: refill it with the slab STAGES further down the panel's (tile, t) order
+            int pt = t + STAGES, ptile = tile;
+            if (pt >= T) { pt -= T; ptile++; }
+#ifdef GPSLC_PHASE_TIMING
+            const long long _p0 = clock64();
+#endif
+            issue_row_slab(sm, scratch, j, T, blk0, blk_end, ptile, pt, gi + STAGES);
+#ifdef GPSLC_PHASE_TIMING
+            _prod += clock64() - _p0;
+#endif
+        }
     }
 #pragma unroll
     for (int mi = 0; mi < MI; mi++)
@@ -341,6 +366,13 @@ __device__ __noinline__ void row_tile_kloop(double* __restrict__ accio, const do
             accio[(mi * 8 + ni) * 2] = acc[mi][ni][0];
             accio[(mi * 8 + ni) * 2 + 1] = acc[mi][ni][1];
         }
+#ifdef GPSLC_PHASE_TIMING
+    if (lane == 0) {   // all warps: slots 12/13/14 are sums over the 8 warps
+        atomicAdd(&g_phase_cycles[12], (unsigned long long)_wait);
+        atomicAdd(&g_phase_cycles[13], (unsigned long long)(clock64() - _f0));
+        atomicAdd(&g_phase_cycles[14], (unsigned long long)_prod);
+    }
+#endif
 }
 
 // Gen concept:
@@ -386,23 +418,22 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
             double wsum[MAXRHS] = {0.0, 0.0};
             double wsnap[MAXRHS] = {0.0, 0.0};  // residual after the leading snapJ panels only (ITE: -MeanITE)
             const int wr = tid >> 2, kq = tid & 3;  // RHS update mapping: row wr, k pair kq
-            // every thread tracks the producer counter; the issuing lane rotates over the warps so that no single warp carries
-            // the whole producer overhead (all warps advance in near lockstep through the stage ring)
-            auto produce = [&](int t) {
-                const uint32_t gi = pipe.produced++;
-                if (lane != 0 || warp != (int)(gi & (FWARPS - 1))) return;
+            // operand slab t of the diagonal block row goes into pipeline slot gi (stage known to be free); the first STAGES
+            // slabs are issued here, the others by the last warp that leaves the stage they reuse
+            auto issue_diag_slab = [&](const int t, const uint32_t gi) {
                 const int st = gi % STAGES;
-                if (gi >= STAGES) mbar_wait(&sm.empty[st], ((gi / STAGES) - 1) & 1);
                 mbar_expect_tx(&sm.full[st], SLAB_D * 8);
                 bulk_g2s(sm.stage + st * STAGE_D + 2 * SLAB_D, scratch + row_off(j) + (size_t)t * SLAB_D, SLAB_D * 8, &sm.full[st]);
             };
-            for (int t = 0; t < PF && t < T; t++) produce(t);
+            for (int t = 0; t < STAGES && t < T; t++) {
+                const uint32_t gi = pipe.consumed + t;
+                if (lane == 0 && warp == (int)(gi & (FWARPS - 1))) issue_diag_slab(t, gi);
+            }
             const bool in_tail = SNAP && (j >= snapJ);
             const bool do_snap = in_tail && (snap != nullptr) && (trank == 0);
             const int Tsnap = in_tail ? snapJ * NSLAB : T;
             auto kloop = [&](const int tb, const int te) {
                 for (int t = tb; t < te; t++) {
-                    if (t + PF < T) produce(t + PF);
                     const uint32_t gi = pipe.consumed++;
                     const int st = gi % STAGES;
                     mbar_wait(&sm.full[st], (gi / STAGES) & 1);
@@ -428,7 +459,7 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                         }
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&sm.empty[st]);
+                    if (lane == 0 && stage_release_is_last(&sm.freed[st]) && t + STAGES < T) issue_diag_slab(t + STAGES, gi + STAGES);
                 }
             };
             kloop(0, Tsnap);
@@ -532,8 +563,8 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
         const int blk_end = blk0 + nblk;
         const int ntile = (nblk + 1) >> 1;
         const int F = ntile * T;
-        // prologue of the operand pipeline: the first PF slabs of the panel (the k-loops issue the rest as they go)
-        for (int f = 0; f < PF && f < F; f++) {
+        // prologue of the operand pipeline: the first STAGES slabs of the panel (the k-loops issue the rest as they go)
+        for (int f = 0; f < STAGES && f < F; f++) {
             const uint32_t gi = pipe.consumed + f;
             if (lane == 0 && warp == (int)(gi & (FWARPS - 1))) issue_row_slab(sm, scratch, j, T, blk0, blk_end, f / T, f % T, gi);
         }

@@ -26,3 +26,5 @@ print(f"n={n} nX={nX} chains={C}: thread-0 cycles per phase, fraction of the CTA
 for k in (0, 1, 5, 8, 9, 10, 11, 6, 2, 3, 4):
     print(f"  {names[k]:40s} {100 * v[k] / tot:6.2f} %")
 print(f"  {'outside factor_run':40s} {100 * (tot - v[[0, 1, 5, 6, 2, 3, 4]].sum()) / tot:6.2f} %")
+print(f"  row k-loop, per-warp average: waiting for operands (full barrier) {100 * v[12] / v[13]:.2f} % of the loop, "
+      f"elected producer (empty barrier + TMA issue) {100 * v[14] / v[13]:.2f} %")
