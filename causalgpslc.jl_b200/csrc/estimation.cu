@@ -336,9 +336,9 @@ sate_kernel(EstArgs a, double* scratch, size_t slot_scratch, double* zbuf, size_
             // Kp as an RBF factor with the T dimension appended
             rspec.D = spec.D + 1; rspec.n = a.n; rspec.scale = spec.yScale; rspec.noise = spec.yNoise;
             rspec.y[0] = a.Y; rspec.y[1] = d1;
-            rspec.feat[spec.D] = a.T; rspec.w[spec.D] = spec.wT;
+            rspec.feat[spec.D] = a.T; rspec.w[spec.D] = spec.wT; rspec.sw[spec.D] = sqrt(spec.wT);
         }
-        for (int k = threadIdx.x; k < spec.D; k += blockDim.x) { rspec.feat[k] = spec.feat[k]; rspec.w[k] = spec.w[k]; }
+        for (int k = threadIdx.x; k < spec.D; k += blockDim.x) { rspec.feat[k] = spec.feat[k]; rspec.w[k] = spec.w[k]; rspec.sw[k] = sqrt(spec.w[k]); }
         __syncthreads();
         RbfGen rgen{&rspec};
         factor_run(rgen, NCB, NCB, 2, my_scratch, my_z, sm, pipe);

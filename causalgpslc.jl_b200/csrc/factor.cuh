@@ -59,6 +59,7 @@ struct __align__(128) FactorSmem {
     double stage[STAGES * STAGE_D];    // 72 KB; P2 aliases it as workspace while no copy is in flight
     double linv[LINV_D];               // 18 KB; inverse of the current diagonal block: the 72 8x4 atoms on/below the diagonal
     double colfeat[CF_DIMS * NB];      // 12 KB; feature values of the current panel's 64 columns (covariance generation)
+    double exp2tab[32];                // 2^(i/32) for the generators' exponential; must directly follow colfeat
     double wvec[MAXRHS][NB];           // w_j (pre-solve) / scratch
     double part[4][NB];                // per-row partial sums: log L_ii, z0.z0, z0.z1, z1.z1 (kept out of registers)
     double* snap; int snapJ, snap_n;   // snapshot hook parameters
@@ -149,7 +150,17 @@ __device__ __host__ inline int elem_off(int r, int c) {
 __device__ __forceinline__ int linv_off(int n, int k) { return ((n >> 3) * ((n >> 3) + 1) + (k >> 2)) * 32 + (n & 7) * 4 + (k & 3); }
 __device__ __forceinline__ bool linv_has(int n, int k) { return (k >> 2) <= 2 * (n >> 3) + 1; }
 
+// 2^(i/32), correctly rounded (see exp_neg_tab in gens.cuh)
+static __device__ const double GPSLC_EXP2_TAB[32] = {
+    1, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237, 1.0905077326652577, 1.1143867425958924, 1.1387886347566916,
+    1.1637248587775775, 1.189207115002721, 1.215247359980469, 1.241857812073484, 1.2690509571917332, 1.2968395546510096,
+    1.3252366431597413, 1.3542555469368927, 1.383909881963832, 1.4142135623730951, 1.4451808069770467, 1.4768261459394993,
+    1.5091644275934228, 1.5422108254079407, 1.5759808451078865, 1.6104903319492543, 1.6457554781539649, 1.681792830507429,
+    1.7186192981224779, 1.7562521603732995, 1.7947090750031072, 1.8340080864093424, 1.8741676341103, 1.9152065613971474,
+    1.9571441241754002};
+
 __device__ inline void factor_smem_init(FactorSmem& sm) {
+    if (threadIdx.x < 32) sm.exp2tab[threadIdx.x] = GPSLC_EXP2_TAB[threadIdx.x];
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&sm.full[s], 1); sm.freed[s] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

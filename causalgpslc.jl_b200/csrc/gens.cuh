@@ -39,11 +39,37 @@ __device__ __forceinline__ double exp_neg(double a) {
     return (k < -1020) ? 0.0 : v;
 }
 
+// exp(-a), a >= 0, with fewer FP64-pipe instructions (11 instead of ~20: the covariance generation shares that pipe with the
+// DMMAs): x = -a = (32 e + i) ln2/32 + r with |r| <= ln2/64, exp(x) = 2^e * 2^(i/32) * P6(r). 2^(i/32) comes from a 32-entry
+// table in shared memory (correctly rounded entries), the integer part of x 32/ln2 from the low word of the magic-number sum,
+// the Taylor polynomial of degree 6 truncates at 3.5e-18. Max error ~2 ulp. Results below 2^-1020 are flushed to zero.
+__device__ __forceinline__ double exp_neg_tab(double a, const double* tab) {
+    const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52: the sum's low word is round(x * 32/ln2)
+    const double t = fma(-a, 46.16624130844683, MAGIC);
+    const int k = __double2loint(t);
+    const double kd = t - MAGIC;
+    double r = fma(kd, -0.02166084938653512, -a);          // ln2/32, upper 32 bits (kd * hi is exact)
+    r = fma(kd, -5.9631716539705866e-12, r);
+    double p = 1.0 / 720.0;
+    p = fma(p, r, 1.0 / 120.0);
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double v = tab[k & 31] * p;
+    const int e = k >> 5;
+    const double out = __hiloint2double(__double2hiint(v) + (e << 20), __double2loint(v));
+    // a > 745 (integer compare on the high word: a >= 0) would wrap k; anything below 2^-1020 is flushed
+    return (__double2hiint(a) >= 0x40874800 || e < -1020) ? 0.0 : out;
+}
+
 // K[r][c] = scale * exp(-sum_d w_d (f_d[r]-f_d[c])^2) + noise*[r==c],  w_d = 1/ls_d^2  (no 1/2, lengthscale squared:
 // src/kernel.jl:17). Rows/cols >= n are identity padding.
 struct RbfSpec {
     const double* feat[DMAX];
     double w[DMAX];
+    double sw[DMAX];    // sqrt(w_d) = 1 / lengthscale_d: the tile generator works on pre-scaled features, (sw f_r - sw f_c)^2
     const double* y[MAXRHS];
     double scale, noise;
     int D, n;
@@ -97,7 +123,7 @@ struct RbfGen {
         if (!GPSLC_STAGE_COLS || D > CF_DIMS) return;
         for (int i = threadIdx.x; i < D * NB; i += blockDim.x) {
             const int d = i >> 6, c = col0 + (i & 63);
-            cf[i] = (c < s->n) ? __ldg(s->feat[d] + c) : 0.0;
+            cf[i] = (c < s->n) ? __ldg(s->feat[d] + c) * s->sw[d] : 0.0;    // pre-scaled by 1 / lengthscale
         }
     }
     template <int NI, bool ONE_ROW>
@@ -112,9 +138,9 @@ struct RbfGen {
 #pragma unroll 4
             for (int d = 0; d < D; d++) {
                 const double* p = s->feat[d];
-                const double w = s->w[d];
-                const double z0 = __ldg(p + r0);
-                const double z1 = ONE_ROW ? z0 : __ldg(p + r1);
+                const double w = s->sw[d];
+                const double z0 = __ldg(p + r0) * w;
+                const double z1 = ONE_ROW ? z0 : __ldg(p + r1) * w;
 #pragma unroll
                 for (int ni = 0; ni < NI; ni++) {
                     double c0v, c1v;
@@ -122,26 +148,27 @@ struct RbfGen {
                         const double2 cc = *reinterpret_cast<const double2*>(cf + d * NB + cl + 8 * ni);
                         c0v = cc.x; c1v = cc.y;
                     } else {
-                        c0v = __ldg(p + c0 + 8 * ni); c1v = __ldg(p + c0 + 8 * ni + 1);
+                        c0v = __ldg(p + c0 + 8 * ni) * w; c1v = __ldg(p + c0 + 8 * ni + 1) * w;
                     }
                     double t;
-                    t = z0 - c0v; a[0][ni][0] = fma(t * w, t, a[0][ni][0]);
-                    t = z0 - c1v; a[0][ni][1] = fma(t * w, t, a[0][ni][1]);
+                    t = z0 - c0v; a[0][ni][0] = fma(t, t, a[0][ni][0]);
+                    t = z0 - c1v; a[0][ni][1] = fma(t, t, a[0][ni][1]);
                     if (!ONE_ROW) {
-                        t = z1 - c0v; a[1][ni][0] = fma(t * w, t, a[1][ni][0]);
-                        t = z1 - c1v; a[1][ni][1] = fma(t * w, t, a[1][ni][1]);
+                        t = z1 - c0v; a[1][ni][0] = fma(t, t, a[1][ni][0]);
+                        t = z1 - c1v; a[1][ni][1] = fma(t, t, a[1][ni][1]);
                     }
                 }
             }
             const double sc = s->scale, nz = s->noise;
+            const double* tab = cf + CF_DIMS * NB;   // FactorSmem::exp2tab follows colfeat
 #pragma unroll
             for (int ni = 0; ni < NI; ni++) {
                 const int c = c0 + 8 * ni;
-                v[0][ni][0] = sc * exp_neg(a[0][ni][0]) + ((r0 == c) ? nz : 0.0);
-                v[0][ni][1] = sc * exp_neg(a[0][ni][1]) + ((r0 == c + 1) ? nz : 0.0);
+                v[0][ni][0] = fma(sc, exp_neg_tab(a[0][ni][0], tab), (r0 == c) ? nz : 0.0);
+                v[0][ni][1] = fma(sc, exp_neg_tab(a[0][ni][1], tab), (r0 == c + 1) ? nz : 0.0);
                 if (!ONE_ROW) {
-                    v[1][ni][0] = sc * exp_neg(a[1][ni][0]) + ((r1 == c) ? nz : 0.0);
-                    v[1][ni][1] = sc * exp_neg(a[1][ni][1]) + ((r1 == c + 1) ? nz : 0.0);
+                    v[1][ni][0] = fma(sc, exp_neg_tab(a[1][ni][0], tab), (r1 == c) ? nz : 0.0);
+                    v[1][ni][1] = fma(sc, exp_neg_tab(a[1][ni][1], tab), (r1 == c + 1) ? nz : 0.0);
                 }
             }
         } else {

@@ -166,6 +166,7 @@ batched_logpdf_kernel(int batch, int n, const double* __restrict__ Kall, int ld,
             for (int d = threadIdx.x; d < D; d += blockDim.x) {
                 spec.feat[d] = feat + (size_t)b * feat_stride + (size_t)d * n;
                 spec.w[d] = w[(size_t)b * D + d];
+                spec.sw[d] = sqrt(spec.w[d]);
             }
             __syncthreads();
             RbfGen gen{&spec};

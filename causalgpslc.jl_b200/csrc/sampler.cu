@@ -84,6 +84,7 @@ __device__ inline void build_spec(const ModelDev& m, const ChainDev& c, int chai
         const int p = fd.ls_param[d];
         const double ls = (p == ov_param) ? ov_val : theta[p];
         spec->w[d] = 1.0 / (ls * ls);
+        spec->sw[d] = 1.0 / ls;
     }
     if (threadIdx.x == 0) {
         spec->D = fd.D;
