@@ -25,6 +25,7 @@ import numpy as np  # noqa: E402
 
 WORKLOAD = dict(name="c3", n=1024, n_obj=16, nX=10, nU=1, chains_per_gpu=512)
 FP64_PEAK_FILE = os.path.join(ROOT, "profiles", "fp64_peak_r01.json")
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")   # dram bytes per mh_lanes launch from `ncu --set full`
 
 
 def synthetic(n, n_obj, nX, seed=1234):
@@ -98,6 +99,13 @@ def fp64_peak():
         return float(d["dgemm8192_tflops_sustained"]), "profiles/fp64_peak_r01.json (cuBLAS DGEMM 8192^3 sustained on this pool's B200; MEASURED_PEAKS.json has no FP64 entry)"
     except Exception:
         return 37.0, "nominal FP64 fallback (no measured file)"
+
+
+def ncu_traffic():
+    try:
+        return float(json.load(open(TRAFFIC_FILE))["dram_bytes_per_launch"])
+    except Exception:
+        return None
 
 
 def cpu_sample(steps_sites=6, threads=None):
@@ -226,6 +234,31 @@ def run_ours(args):
     h2d = (X.size + T.size + Y.size) * 8 + 4 * len(counts) + 27 * 8
     d2h = out.size * 8
 
+    # ---- second half of BASELINE.json's metric: ITE samples/sec. One ITE sample = one length-n draw from N(MeanITE, CovITE)
+    # (src/estimation.jl:105). The current state of every chain serves as one retained posterior sample: C tasks, each one
+    # augmented 2n x 2n Cholesky + spp draws, through the host-buffer C ABI (H2D of the samples, D2H of the draws included).
+    ite = None
+    if not args.no_e2e:
+        from gpslc_b200 import estimation as ge
+        spp = 10
+        packed = smp.state()[None, :, :]
+        ret0 = np.zeros(1, dtype=np.int32)
+        ge.ite(packed[:, :8], X, T, Y, w["nU"], 0.0, ret0, 1e-10, spp, seed=1, chain_offset=rank * C, ctx=ctx)   # warm-up
+        barrier()
+        ti = time.perf_counter()
+        o = ge.ite(packed, X, T, Y, w["nU"], 0.0, ret0, 1e-10, spp, seed=1, chain_offset=rank * C, ctx=ctx)
+        barrier()
+        ti = time.perf_counter() - ti
+        if world > 1:
+            tt = torch.tensor([ti], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ti = float(tt.item())
+        nI = w["n"]
+        ite = {"value": world * C * spp / ti, "unit": "ITE samples/s", "seconds": ti,
+               "workload": f"sampleITE(doT=0) for {C} posterior samples per GPU (one per chain) x {spp} draws at n={nI}: "
+                           "one fused 2n x 2n Cholesky per sample; host buffers in, draws out",
+               "tflops": world * C * (8.0 * nI ** 3 / 3.0) / ti / 1e12, "all_pd": bool(o["info"].max() == 0)}
+
     if rank == 0:
         n = w["n"]
         flops_per_factor = n ** 3 / 3.0 + 2.0 * n * n
@@ -245,10 +278,10 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": "sweeps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "call": f"Posterior(host X,T,Y; nOuter=1, nMHInner={e2e_sweeps}, nESInner=0, {C} chains) incl. generate + H2D + D2H"},
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                             "traffic": None, "kernel": "mh_lanes_kernel (fused RBF build + blocked Cholesky + solve, DMMA)",
+                             "traffic": ncu_traffic(), "kernel": "mh_lanes_kernel (fused RBF build + blocked Cholesky + solve, DMMA)",
                              "algorithmic": f"{S - 1} factors x (n^3/3 + 2n^2) flops x {C} chains per launch",
                              "peak_source": peak_src},
-                "mh_accept_rate": float(acc.sum() / max(1, C * S * (args.warmup + args.steps)))}
+                "mh_accept_rate": float(acc.sum() / max(1, C * S * (args.warmup + args.steps))), "ite": ite}
         # ---- CPU baseline on the box's host cores (bounded sample, rank 0 at N=1 only)
         if world == 1 and not args.no_cpu:
             run, Ssites = cpu_sample()
