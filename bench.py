@@ -153,7 +153,7 @@ def run_reference(args):
             "config": {"workload": "c3: n=1024, 16 objects, nX=10, nU=1; one chain on the host (the reference is single-chain, single-process)"},
             "cpu_baseline": {"value": value, "unit": "sweeps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_ours(args):
@@ -292,7 +292,7 @@ def run_ours(args):
                                     "sample": f"{nsite} of {Ssites} single-site MH updates of one sweep of one chain at the c3 shape, "
                                               "reference cost model (full model re-score per update), NumPy/SciPy oracle port with "
                                               f"BLAS threads = all {os.cpu_count()} host cores; {tc:.1f} s of CPU work"}
-        print(json.dumps(line))
+        emit(line)
     smp.close()
     ctx.close()
     if world > 1:
@@ -300,7 +300,27 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Everything libraries print to fd 1 (e.g. NCCL's version banner) goes to stderr; the JSON line alone goes to stdout."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -375,6 +375,21 @@ int gpslc_ite(gpslc_ctx* h, int loc, const gpslc_data* d, const double* samples,
     return est_common(h, loc, d, samples, n_outer, n_chains, stride, ret_idx, R, doT, n_doT, jitter, spp, seed, chain_offset, 0,
                       false, meanITE, covITE, ite, info);
 }
+int gpslc_summarize(gpslc_ctx* h, int loc, const double* samples, int batch, int m, int n, double credible_interval, double* out) {
+    if (!h) return GPSLC_ERR_ARG;
+    Ctx* ctx = &h->c;
+    if (!samples || !out || batch < 0 || m <= 0 || n <= 0 || !(credible_interval > 0.0 && credible_interval < 1.0))
+        return ctx->fail(GPSLC_ERR_ARG, "gpslc_summarize: bad argument");
+    if (batch == 0) return GPSLC_OK;
+    GP_CUDA(ctx, cudaSetDevice(ctx->device));
+    Staged<double> dS(ctx), dO(ctx);
+    GP_TRY(dS.in(loc, samples, (size_t)batch * m * n));
+    GP_TRY(dO.outbuf(loc, out, (size_t)batch * n * 3));
+    GP_TRY(launch_summarize(ctx, dS.d, batch, m, n, credible_interval, dO.d));
+    GP_TRY(dO.finish());
+    GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GPSLC_OK;
+}
 int gpslc_sate(gpslc_ctx* h, int loc, const gpslc_data* d, const double* samples, int n_outer, int n_chains, int stride,
                const int* ret_idx, int R, const double* doT, int n_doT, double jitter, int spp, uint64_t seed, int chain_offset,
                int var_as_std, double* meanSATE, double* varSATE, double* sate, int* info) {

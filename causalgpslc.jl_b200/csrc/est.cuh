@@ -20,4 +20,7 @@ struct EstArgs {
     int var_as_std;
 };
 
+struct Ctx;
+int launch_summarize(Ctx* ctx, const double* samples, int batch, int m, int n, double ci, double* out);
+
 }  // namespace gpslc

@@ -435,4 +435,70 @@ int launch_sate(Ctx* ctx, const EstArgs& a) {
     return GPSLC_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ summarizeEstimates
+// One CTA per (batch element, tile of IT individuals): the tile's samples are staged through shared memory with coalesced
+// loads (individual fastest), each warp then bitonic-sorts the rows it owns and lane 0 interpolates the two quantiles
+// (src/driver.jl:129-149; Julia `quantile` default = type 7). HBM-bound: every sample is read once (8 m n bytes per batch
+// element), 24 n bytes written.
+__global__ void __launch_bounds__(256) summarize_kernel(const double* __restrict__ samples, int m, int mpad, int n, int IT, double lowerQ,
+                                                        double upperQ, double* __restrict__ out) {
+    extern __shared__ double tile[];   // [IT][mpad]
+    const int b = blockIdx.y, i0 = blockIdx.x * IT;
+    const double* src = samples + (size_t)b * m * n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int e = threadIdx.x; e < IT * mpad; e += blockDim.x) {
+        const int s = e / IT, ii = e - s * IT;
+        tile[ii * mpad + s] = (s < m && i0 + ii < n) ? src[(size_t)s * n + i0 + ii] : INFINITY;
+    }
+    __syncthreads();
+    for (int ii = warp; ii < IT && i0 + ii < n; ii += nwarps) {
+        double* x = tile + ii * mpad;
+        for (int k = 2; k <= mpad; k <<= 1) {
+            for (int jj = k >> 1; jj > 0; jj >>= 1) {
+                for (int t = lane; t < (mpad >> 1); t += 32) {
+                    const int lo = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));   // element index with bit jj cleared
+                    const int hi = lo | jj;
+                    const bool up = ((lo & k) == 0);
+                    const double a = x[lo], c = x[hi];
+                    if ((a > c) == up) { x[lo] = c; x[hi] = a; }
+                }
+                __syncwarp();
+            }
+        }
+        double sum = 0.0;
+        for (int t = lane; t < m; t += 32) sum += x[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) {
+            double* o3 = out + ((size_t)b * n + i0 + ii) * 3;
+            o3[0] = sum / m;
+            const double qs[2] = {lowerQ, upperQ};
+            for (int qi = 0; qi < 2; qi++) {
+                const double h = (m - 1) * qs[qi];
+                int l = (int)floor(h);
+                l = max(0, min(l, m - 1));
+                const int u = min(l + 1, m - 1);
+                o3[1 + qi] = x[l] + (h - l) * (x[u] - x[l]);
+            }
+        }
+    }
+}
+
+int launch_summarize(Ctx* ctx, const double* samples, int batch, int m, int n, double ci, double* out) {
+    int mpad = 2;
+    while (mpad < m) mpad <<= 1;
+    if (mpad > 8192) return ctx->fail(GPSLC_ERR_UNSUPPORTED, "gpslc_summarize: more than 8192 samples per individual");
+    int IT = (int)((192 * 1024) / ((size_t)mpad * sizeof(double)));
+    if (IT > 32) IT = 32;
+    if (IT > n) IT = n;
+    const size_t smem = (size_t)IT * mpad * sizeof(double);
+    GP_CUDA(ctx, cudaFuncSetAttribute(summarize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const double lowerQ = (1.0 - ci) / 2.0, upperQ = 1.0 - lowerQ;
+    dim3 grid(ceil_div(n, IT), batch);
+    summarize_kernel<<<grid, 256, smem, ctx->stream>>>(samples, m, mpad, n, IT, lowerQ, upperQ, out);
+    ctx->launches++;
+    GP_CUDA(ctx, cudaGetLastError());
+    return GPSLC_OK;
+}
+
 }  // namespace gpslc

@@ -98,14 +98,15 @@ def sampleSATE(g, doT, samplesPerPosterior=10, all_chains=False, var_as_std=True
     return o["samples"][0] if all_chains else o["samples"][0, 0]
 
 
-def summarizeEstimates(samples, savetofile="", credible_interval=0.90):
-    """src/driver.jl:129-149 (host-side summary, outside the GPU hot path): DataFrame Individual/Mean/LowerBound/UpperBound."""
+def summarizeEstimates(samples, savetofile="", credible_interval=0.90, ctx=None):
+    """src/driver.jl:129-149: DataFrame Individual/Mean/LowerBound/UpperBound from the n x m matrix sampleITE returns. The
+    row statistics (mean, two type-7 quantiles) are computed by the CUDA library (gpslc_summarize)."""
     import pandas as pd
-    lowerQ = (1 - credible_interval) / 2
-    upperQ = 1 - lowerQ
+    from .estimation import summarize
     samples = np.asarray(samples, dtype=np.float64)
-    df = pd.DataFrame({"Individual": np.arange(1, samples.shape[0] + 1), "Mean": samples.mean(axis=1),
-                       "LowerBound": np.quantile(samples, lowerQ, axis=1), "UpperBound": np.quantile(samples, upperQ, axis=1)})
+    st = summarize(np.ascontiguousarray(samples.T), credible_interval, ctx=ctx)      # [n, 3]
+    df = pd.DataFrame({"Individual": np.arange(1, samples.shape[0] + 1), "Mean": st[:, 0], "LowerBound": st[:, 1],
+                       "UpperBound": st[:, 2]})
     if savetofile != "":
         df.to_csv(savetofile, index=False)
         print("Saved mean and 90% credible intervals to " + savetofile)

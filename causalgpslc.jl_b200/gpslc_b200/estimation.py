@@ -22,6 +22,8 @@ def _bind_est(lib):
     lib.gpslc_ite.argtypes = [vp, i, P(GpslcData), vp, i, i, i, vp, i, vp, i, dbl, i, u64, i, vp, vp, vp, vp]
     lib.gpslc_sate.restype = i
     lib.gpslc_sate.argtypes = [vp, i, P(GpslcData), vp, i, i, i, vp, i, vp, i, dbl, i, u64, i, i, vp, vp, vp, vp]
+    lib.gpslc_summarize.restype = i
+    lib.gpslc_summarize.argtypes = [vp, i, vp, i, i, i, dbl, vp]
     lib._est_bound = True
 
 
@@ -77,3 +79,19 @@ def sate(samples, X, T, Y, nU, doT, ret_idx, jitter, spp, seed=0, chain_offset=0
                                  float(jitter), int(spp), int(seed), int(chain_offset), int(bool(var_as_std)), ptr(mean), ptr(var),
                                  ptr(smp), ptr(info)))
     return {"mean": mean, "var": var, "samples": smp, "info": info}
+
+
+def summarize(samples, credible_interval=0.90, ctx=None):
+    """gpslc_summarize: samples [batch, m, n] (or [m, n]) -> [batch, n, 3] (or [n, 3]) = Mean, LowerBound, UpperBound per
+    individual; the device-side body of summarizeEstimates (src/driver.jl:129-149)."""
+    from .kernel import default_context
+    ctx = ctx or default_context()
+    _bind(ctx.lib); _bind_est(ctx.lib)
+    s = np.ascontiguousarray(samples, dtype=np.float64)
+    squeeze = s.ndim == 2
+    if squeeze:
+        s = s[None]
+    batch, m, n = s.shape
+    out = np.empty((batch, n, 3))
+    ctx.check(ctx.lib.gpslc_summarize(ctx.h, HOST, ptr(s), batch, m, n, float(credible_interval), ptr(out)))
+    return out[0] if squeeze else out

@@ -188,6 +188,16 @@ int gpslc_sate(gpslc_ctx* ctx, int loc, const gpslc_data* data, const double* sa
                const int* ret_idx, int R, const double* doT, int n_doT, double jitter, int spp, uint64_t seed, int chain_offset,
                int var_as_std, double* meanSATE, double* varSATE, double* sate, int* info);
 
+/* summarizeEstimates (src/driver.jl:129-149): for every individual the mean and the (1-ci)/2 and 1-(1-ci)/2 quantiles of its
+ * m samples, Julia's default `quantile` (linear interpolation between order statistics, type 7; KAT test/driver.jl:54-71).
+ *   samples [batch][m][n]  — the layout gpslc_ite writes (`ite` for one doT and one chain is one batch element with
+ *                            m = R*spp; for one doT and all chains pooled, m = n_chains*R*spp)
+ *   out     [batch][n][3]  — Mean, LowerBound, UpperBound
+ * With loc = GPSLC_DEVICE a counterfactual sweep is summarised where gpslc_ite left it in HBM (BASELINE config c5 never
+ * ships its 168 MB of draws to the host). m <= 8192. */
+int gpslc_summarize(gpslc_ctx* ctx, int loc, const double* samples, int batch, int m, int n, double credible_interval,
+                    double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -288,6 +288,27 @@ def test_zero_effect_identity_through_c_abi(ctx, kats):
         assert np.all(s["mean"] == 0.0) and np.allclose(s["var"], jit, rtol=1e-12)
 
 
+def test_summarize_estimates_on_device(ctx, kats):
+    """gpslc_summarize vs the reference's quantile KAT (test/driver.jl:54-71) and vs the oracle (NumPy type-7 quantiles) on
+    ragged shapes: one sample, non-power-of-two sample counts, a single individual, several batch elements."""
+    k = kats["summarizeEstimates_quantiles"]
+    samples = np.array(k["samples"], dtype=float)[None, :]
+    for ci, (lo, hi) in k["intervals"].items():
+        df = g.summarizeEstimates(samples, credible_interval=float(ci), ctx=ctx)
+        assert np.isclose(df["LowerBound"][0], lo, rtol=1e-13) and np.isclose(df["UpperBound"][0], hi, rtol=1e-13)
+        assert np.isclose(df["Mean"][0], samples.mean(), rtol=1e-13)
+    rng = np.random.default_rng(5)
+    for batch, m, n in ((1, 1, 1), (1, 2, 5), (3, 10, 33), (2, 150, 272), (1, 1000, 70), (1, 4097, 3), (4, 10, 2048)):
+        x = rng.standard_normal((batch, m, n)) * 3 + 1
+        got = ge.summarize(x, 0.9, ctx=ctx)
+        for b in range(batch):
+            mean, lb, ub = oe.summarize_estimates(x[b].T, 0.9)
+            assert np.allclose(got[b, :, 0], mean, rtol=1e-12, atol=1e-13)
+            assert np.allclose(got[b, :, 1], lb, rtol=1e-12, atol=1e-13) and np.allclose(got[b, :, 2], ub, rtol=1e-12, atol=1e-13)
+    with pytest.raises(Exception):
+        ge.summarize(np.zeros((1, 9000, 2)), 0.9, ctx=ctx)      # more than 8192 samples per individual: refused loudly
+
+
 # ------------------------------------------------------------------------------------------------ public API end to end
 def test_public_api_shapes_and_golden_gate(ctx, kats):
     """gpslc(csv) -> sampleITE(g, 0.6) -> summarizeEstimates: >= 50% of the 150 individuals' mean ITE inside the

@@ -112,11 +112,3 @@ def test_prepare_data_matches_oracle(kats):
 def test_to_matrix_mirror_matches_oracle():
     U = [np.arange(11, 17.0), np.arange(21, 27.0)]
     assert np.array_equal(g.toMatrix(U, 6, 2), om.to_matrix(U, 6, 2))
-
-
-def test_summarize_estimates_quantile_kat(kats):
-    k = kats["summarizeEstimates_quantiles"]
-    samples = np.array(k["samples"], dtype=float)[None, :]
-    for ci, (lo, hi) in k["intervals"].items():
-        df = g.summarizeEstimates(samples, credible_interval=float(ci))
-        assert np.isclose(df["LowerBound"][0], lo) and np.isclose(df["UpperBound"][0], hi)
