@@ -22,7 +22,7 @@ namespace gpslc {
 // Development aid (-DGPSLC_PHASE_TIMING, tools/gpu_phase_timing.py): cycles thread 0 of every CTA spends in each phase of
 // factor_run, accumulated in a per-translation-unit device array. Compiles to nothing in the product build.
 #ifdef GPSLC_PHASE_TIMING
-static __device__ unsigned long long g_phase_cycles[16];
+static __device__ unsigned long long g_phase_cycles[24];
 #define GP_PHASE_INIT() long long _pt = clock64()
 #define GP_PHASE_MARK(k) do { if (threadIdx.x == 0) { const long long _n = clock64(); atomicAdd(&g_phase_cycles[k], (unsigned long long)(_n - _pt)); _pt = _n; } } while (0)
 #else
@@ -180,6 +180,18 @@ __device__ inline void factor_smem_init(FactorSmem& sm) {
 // 64-pivot chain is tensor work on purpose: while the sibling CTA streams DMMAs, the serial warp issues roughly one
 // instruction per 7 cycles (measured), so this phase is paid for per instruction.
 // Returns via sm.info the first non-positive pivot (1-based global column), if any.
+// 1/sqrt(a) for a normal positive a in 5 FP64 instructions (the library routine takes 11): hardware seed (relative error
+// < 2^-22) and one third-order step y (1 + e/2 + 3e^2/8), e = 1 - a y^2, which leaves ~2^-66 before rounding. Every FP64
+// instruction of the pivot chain queues behind the sibling CTA's DMMAs, so the count is what matters here.
+__device__ __forceinline__ double rsqrt_fast(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double t = a * y;
+    const double e = fma(-t, y, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    const double ye = y * e;
+    return fma(ye, p, y);
+}
 __device__ __forceinline__ double neg_bits(double x) { return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x)); }
 
 __device__ inline void p2_factor_diag(FactorSmem& sm, double* Cs, int col0) {
@@ -190,56 +202,83 @@ __device__ inline void p2_factor_diag(FactorSmem& sm, double* Cs, int col0) {
     // plain SHFLs instead of WARPSYNC.COLLECTIVE sequences
     const int warp_u = __shfl_sync(FULL, warp, 0);
     GP_PHASE_INIT();
-    for (int kb = 0; kb < 8; kb++) {
+    // 8x8 Cholesky + inverse of diagonal tile kb by the calling warp (registers + shuffles)
+    auto potf2 = [&](const int kb) {
         const int c0 = kb * 8;
-        if (warp_u == 0) {
-            // lane r (= lane & 7) holds row r of the 8x8 block; afterwards column r of its inverse
-            const int r = lane & 7;
-            double a[8];
+        // lane r (= lane & 7) holds row r of the 8x8 block; afterwards column r of its inverse
+        const int r = lane & 7;
+        double a[8];
+#ifdef GPSLC_PHASE_TIMING
+        long long _q0 = clock64();
+#define GP_SUB(k) do { if (threadIdx.x == 0) { const long long _n = clock64(); atomicAdd(&g_phase_cycles[k], (unsigned long long)(_n - _q0)); _q0 = _n; } } while (0)
+#else
+#define GP_SUB(k) do {} while (0)
+#endif
 #pragma unroll
-            for (int k = 0; k < 8; k++) a[k] = (k <= r) ? Cs[(c0 + r) * CS_LD + c0 + k] : 0.0;
-            double rinv_r = 0.0;
+        for (int k = 0; k < 8; k++) a[k] = (k <= r) ? Cs[(c0 + r) * CS_LD + c0 + k] : 0.0;
+        double rinv_r = 0.0;
+        GP_SUB(16);
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                double akk = __shfl_sync(FULL, a[k], k);
-                if (!(akk > 0.0)) {
-                    if (lane == 0 && sm.info == 0) sm.info = col0 + c0 + k + 1;
-                    akk = 1.0;
-                }
-                const double ri = rsqrt(akk);
-                const double lk = a[k] * ri;
-                a[k] = lk;
-                if (r == k) rinv_r = ri;
-#pragma unroll
-                for (int j = k + 1; j < 8; j++) {
-                    const double ljk = __shfl_sync(FULL, lk, j);
-                    a[j] = fma(-lk, ljk, a[j]);
-                }
+        for (int k = 0; k < 8; k++) {
+            double akk = __shfl_sync(FULL, a[k], k);
+            // positive and finite? (integer test on the high word: no FP64-pipe instruction; NaN and denormal pivots fail it)
+            const int hik = __double2hiint(akk);
+            if (!(hik > 0 && hik < 0x7ff00000)) {
+                if (lane == 0 && sm.info == 0) sm.info = col0 + c0 + k + 1;
+                akk = 1.0;
             }
-            double x[8];
+            const double ri = rsqrt_fast(akk);
+            const double lk = a[k] * ri;
+            a[k] = lk;
+            if (r == k) rinv_r = ri;
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const double rii = __shfl_sync(FULL, rinv_r, i);
-                double s = 0.0;
-#pragma unroll
-                for (int k = 0; k < i; k++) {
-                    const double lik = __shfl_sync(FULL, a[k], i);
-                    s = fma(lik, x[k], s);
-                }
-                x[i] = (i == r) ? rii : ((i > r) ? -s * rii : 0.0);
-            }
-            if (lane < 8) {
-                // x[i] = D[i][r]: atom (ni = kb, kc = 2 kb + r/4), element (i, r%4); zeros above the diagonal are written too
-                double* at = sm.linv + (kb * (kb + 1) + 2 * kb + (r >> 2)) * 32 + (r & 3);
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    if (k <= r) Cs[(c0 + r) * CS_LD + c0 + k] = a[k];
-                    at[k * 4] = x[k];
-                }
+            for (int j = k + 1; j < 8; j++) {
+                const double ljk = __shfl_sync(FULL, lk, j);
+                a[j] = fma(-lk, ljk, a[j]);
             }
         }
-        __syncthreads();
-        GP_PHASE_MARK(8);
+        GP_SUB(17);
+        double x[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const double rii = __shfl_sync(FULL, rinv_r, i);
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < i; k++) {
+                const double lik = __shfl_sync(FULL, a[k], i);
+                s = fma(lik, x[k], s);
+            }
+            x[i] = (i == r) ? rii : ((i > r) ? -s * rii : 0.0);
+        }
+        GP_SUB(18);
+        if (lane < 8) {
+            // x[i] = D[i][r]: atom (ni = kb, kc = 2 kb + r/4), element (i, r%4); zeros above the diagonal are written too
+            double* at = sm.linv + (kb * (kb + 1) + 2 * kb + (r >> 2)) * 32 + (r & 3);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (k <= r) Cs[(c0 + r) * CS_LD + c0 + k] = a[k];
+                at[k * 4] = x[k];
+            }
+        }
+        GP_SUB(19);
+    };
+    // tile (ri, ci) -= X_ri X_ci^T, X = column block kb of the rows below
+    auto update_tile = [&](const int kb, const int ri, const int ci) {
+        const int c0 = kb * 8;
+        const double* arow = Cs + (ri * 8 + g) * CS_LD + c0 + q;
+        const double* brow = Cs + (ci * 8 + g) * CS_LD + c0 + q;
+        double2* cp = reinterpret_cast<double2*>(Cs + (ri * 8 + g) * CS_LD + ci * 8 + 2 * q);
+        const double2 cv = *cp;
+        double acc[2] = {cv.x, cv.y};
+        dmma(acc, neg_bits(arow[0]), brow[0]);
+        dmma(acc, neg_bits(arow[4]), brow[4]);
+        *cp = make_double2(acc[0], acc[1]);
+    };
+    if (warp_u == 0) potf2(0);
+    __syncthreads();
+    GP_PHASE_MARK(8);
+    for (int kb = 0; kb < 8; kb++) {
+        const int c0 = kb * 8;
         // X = A21 D^T for the row tiles below (tile 8 = right-hand-side rows); the result replaces A21 and, negated, fills the
         // sub-diagonal atoms of sm.linv
         {
@@ -260,28 +299,28 @@ __device__ inline void p2_factor_diag(FactorSmem& sm, double* Cs, int col0) {
         }
         __syncthreads();
         GP_PHASE_MARK(9);
-        // trailing update: tile (ri, ci) -= X_ri X_ci^T for kb < ci <= min(ri, 7), ri <= 8; tiles dealt round-robin to the warps
-        {
-            int idx = warp;
+        // trailing update, tiles (ri, ci) with kb < ci <= min(ri, 7), ri <= 8. Warp 0 updates the next diagonal tile first and goes
+        // straight on to its 8x8 factorisation (the serial part of P2) while the other warps share the remaining tiles.
+        if (warp_u == 0) {
+            if (kb < 7) {
+                update_tile(kb, kb + 1, kb + 1);
+                __syncwarp();
+                potf2(kb + 1);
+            }
+        } else {
+            int idx = warp - 1;
             for (int ri = kb + 1; ri <= 8; ri++) {
-                const int width = min(ri, 7) - kb;
+                const int first = (ri == kb + 1) ? 1 : 0;          // tile (kb+1, kb+1) belongs to warp 0
+                const int width = min(ri, 7) - kb - first;
                 while (idx < width) {
-                    const int ci = kb + 1 + idx;
-                    const double* arow = Cs + (ri * 8 + g) * CS_LD + c0 + q;
-                    const double* brow = Cs + (ci * 8 + g) * CS_LD + c0 + q;
-                    double2* cp = reinterpret_cast<double2*>(Cs + (ri * 8 + g) * CS_LD + ci * 8 + 2 * q);
-                    const double2 cv = *cp;
-                    double acc[2] = {cv.x, cv.y};
-                    dmma(acc, neg_bits(arow[0]), brow[0]);
-                    dmma(acc, neg_bits(arow[4]), brow[4]);
-                    *cp = make_double2(acc[0], acc[1]);
-                    idx += FWARPS;
+                    update_tile(kb, ri, kb + 1 + first + idx);
+                    idx += FWARPS - 1;
                 }
                 idx -= width;
             }
         }
         __syncthreads();
-        GP_PHASE_MARK(10);
+        GP_PHASE_MARK(8);
     }
 }
 

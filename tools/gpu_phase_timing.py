@@ -13,7 +13,7 @@ counts, X, T, Y = synthetic(n, n_obj, nX)
 ctx = g.Context(0)
 smp = ChainSampler(default_priors(), X, T, Y, 1, counts, nOuter=24, nMHInner=10, nESInner=5, n_chains=C, seed=1234, ctx=ctx)
 smp.mh_sweeps(1); ctx.synchronize()
-out = (ctypes.c_ulonglong * 16)()
+out = (ctypes.c_ulonglong * 24)()
 ctx.lib.gpslc_debug_phase_cycles(out, 1)
 smp.mh_sweeps(2); ctx.synchronize()
 ctx.lib.gpslc_debug_phase_cycles(out, 1)
@@ -28,3 +28,4 @@ for k in (0, 1, 5, 8, 9, 10, 11, 6, 2, 3, 4):
 print(f"  {'outside factor_run':40s} {100 * (tot - v[[0, 1, 5, 6, 2, 3, 4]].sum()) / tot:6.2f} %")
 print(f"  row k-loop, per-warp average: waiting for operands (full barrier) {100 * v[12] / v[13]:.2f} % of the loop, "
       f"elected producer (empty barrier + TMA issue) {100 * v[14] / v[13]:.2f} %")
+print(f"  8x8 potf2 (warp 0): loads {100 * v[16] / tot:.2f} %, factor loop {100 * v[17] / tot:.2f} %, inverse loop {100 * v[18] / tot:.2f} %, stores {100 * v[19] / tot:.2f} % of the CTA's time")
