@@ -243,12 +243,14 @@ def run_ours(args):
         spp = 10
         packed = smp.state()[None, :, :]
         ret0 = np.zeros(1, dtype=np.int32)
-        ge.ite(packed[:, :8], X, T, Y, w["nU"], 0.0, ret0, 1e-10, spp, seed=1, chain_offset=rank * C, ctx=ctx)   # warm-up
+        ite_reps = 2
+        ge.ite(packed, X, T, Y, w["nU"], 0.0, ret0, 1e-10, spp, seed=1, chain_offset=rank * C, ctx=ctx)   # warm-up (sizes the workspace)
         barrier()
         ti = time.perf_counter()
-        o = ge.ite(packed, X, T, Y, w["nU"], 0.0, ret0, 1e-10, spp, seed=1, chain_offset=rank * C, ctx=ctx)
+        for r in range(ite_reps):
+            o = ge.ite(packed, X, T, Y, w["nU"], 0.0, ret0, 1e-10, spp, seed=2 + r, chain_offset=rank * C, ctx=ctx)
         barrier()
-        ti = time.perf_counter() - ti
+        ti = (time.perf_counter() - ti) / ite_reps
         if world > 1:
             tt = torch.tensor([ti], device="cuda", dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)

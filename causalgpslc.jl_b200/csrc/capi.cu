@@ -318,7 +318,7 @@ int launch_sate(Ctx*, const EstArgs&);
 
 static int est_common(gpslc_ctx* h, int loc, const gpslc_data* d, const double* samples, int n_outer, int n_chains, int stride,
                       const int* ret_idx, int R, const double* doT, int n_doT, double jitter, int spp, uint64_t seed,
-                      int chain_offset, int var_as_std, bool sate, double* o1, double* o2, double* o3, int* info) {
+                      int chain_offset, int var_as_std, bool sate, double* o1, double* o2, double* o3, int* info, int dot_offset = 0) {
     if (!h) return GPSLC_ERR_ARG;
     Ctx* ctx = &h->c;
     if (!d || !samples || !ret_idx || !doT || d->n <= 0 || R < 0 || n_doT < 0 || n_chains <= 0 || spp < 0)
@@ -345,7 +345,7 @@ static int est_common(gpslc_ctx* h, int loc, const gpslc_data* d, const double* 
     a.n = n; a.nX = nX; a.nU = nU; a.n_params = n_params; a.stride = stride;
     a.X = dX.d; a.T = dT.d; a.Y = dY.d; a.samples = dS.d; a.n_chains = n_chains; a.ret_idx = dRet.d; a.R = R;
     a.doT = dDo.d; a.n_doT = n_doT; a.jitter = jitter; a.spp = spp; a.seed = seed; a.chain0 = chain_offset;
-    a.var_as_std = var_as_std;
+    a.var_as_std = var_as_std; a.dot0 = dot_offset;
     GP_TRY(dInfo.outbuf(loc, info, tasks));
     a.info = dInfo.d;
     int rc;
@@ -374,6 +374,20 @@ int gpslc_ite(gpslc_ctx* h, int loc, const gpslc_data* d, const double* samples,
               double* meanITE, double* covITE, double* ite, int* info) {
     return est_common(h, loc, d, samples, n_outer, n_chains, stride, ret_idx, R, doT, n_doT, jitter, spp, seed, chain_offset, 0,
                       false, meanITE, covITE, ite, info);
+}
+int gpslc_ite_slice(gpslc_ctx* h, int loc, const gpslc_data* d, const double* samples, int n_outer, int n_chains, int stride,
+                    const int* ret_idx, int R, const double* doT, int n_doT, int dot_offset, double jitter, int spp, uint64_t seed,
+                    int chain_offset, double* meanITE, double* covITE, double* ite, int* info) {
+    if (dot_offset < 0) return GPSLC_ERR_ARG;
+    return est_common(h, loc, d, samples, n_outer, n_chains, stride, ret_idx, R, doT, n_doT, jitter, spp, seed, chain_offset, 0,
+                      false, meanITE, covITE, ite, info, dot_offset);
+}
+int gpslc_sate_slice(gpslc_ctx* h, int loc, const gpslc_data* d, const double* samples, int n_outer, int n_chains, int stride,
+                     const int* ret_idx, int R, const double* doT, int n_doT, int dot_offset, double jitter, int spp, uint64_t seed,
+                     int chain_offset, int var_as_std, double* meanSATE, double* varSATE, double* sate, int* info) {
+    if (dot_offset < 0) return GPSLC_ERR_ARG;
+    return est_common(h, loc, d, samples, n_outer, n_chains, stride, ret_idx, R, doT, n_doT, jitter, spp, seed, chain_offset,
+                      var_as_std, true, meanSATE, varSATE, sate, info, dot_offset);
 }
 int gpslc_summarize(gpslc_ctx* h, int loc, const double* samples, int batch, int m, int n, double credible_interval, double* out) {
     if (!h) return GPSLC_ERR_ARG;

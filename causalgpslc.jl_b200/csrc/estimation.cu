@@ -229,7 +229,7 @@ ite_kernel(EstArgs a, double* scratch, size_t slot_scratch, double* zbuf, size_t
                 __syncthreads();
                 for (int e = threadIdx.x; e < ns * a.n; e += blockDim.x) {
                     const int s = e / a.n, col = e - s * a.n;
-                    Stream st(a.seed, gchain, (uint32_t)(r * a.spp + s0 + s), stream_b(TAG_ITE, (uint32_t)d));
+                    Stream st(a.seed, gchain, (uint32_t)(r * a.spp + s0 + s), stream_b(TAG_ITE, (uint32_t)(a.dot0 + d)));
                     xi[(size_t)s * a.n + col] = st.normal_at(col);
                 }
                 __syncthreads();
@@ -355,7 +355,7 @@ sate_kernel(EstArgs a, double* scratch, size_t slot_scratch, double* zbuf, size_
                 // normal(mean, var): Gen's second argument is a std, the reference passes the variance (App. B5)
                 const double sd = a.var_as_std ? vs : sqrt(fmax(vs, 0.0));
                 for (int s = 0; s < a.spp; s++) {
-                    Stream st(a.seed, gchain, (uint32_t)(r * a.spp + s), stream_b(TAG_SATE, (uint32_t)d));
+                    Stream st(a.seed, gchain, (uint32_t)(r * a.spp + s), stream_b(TAG_SATE, (uint32_t)(a.dot0 + d)));
                     a.sate_out[((size_t)d * a.n_chains + c) * a.R * a.spp + (size_t)r * a.spp + s] = ms + sd * st.normal();
                 }
             }

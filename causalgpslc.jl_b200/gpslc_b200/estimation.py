@@ -22,6 +22,10 @@ def _bind_est(lib):
     lib.gpslc_ite.argtypes = [vp, i, P(GpslcData), vp, i, i, i, vp, i, vp, i, dbl, i, u64, i, vp, vp, vp, vp]
     lib.gpslc_sate.restype = i
     lib.gpslc_sate.argtypes = [vp, i, P(GpslcData), vp, i, i, i, vp, i, vp, i, dbl, i, u64, i, i, vp, vp, vp, vp]
+    lib.gpslc_ite_slice.restype = i
+    lib.gpslc_ite_slice.argtypes = [vp, i, P(GpslcData), vp, i, i, i, vp, i, vp, i, i, dbl, i, u64, i, vp, vp, vp, vp]
+    lib.gpslc_sate_slice.restype = i
+    lib.gpslc_sate_slice.argtypes = [vp, i, P(GpslcData), vp, i, i, i, vp, i, vp, i, i, dbl, i, u64, i, i, vp, vp, vp, vp]
     lib.gpslc_summarize.restype = i
     lib.gpslc_summarize.argtypes = [vp, i, vp, i, i, i, dbl, vp]
     lib._est_bound = True
@@ -42,9 +46,10 @@ def _data_struct(X, T, Y, nU):
     return d, keep
 
 
-def ite(samples, X, T, Y, nU, doT, ret_idx, jitter, spp, seed=0, chain_offset=0, want_cov=False, want_samples=True, ctx=None):
+def ite(samples, X, T, Y, nU, doT, ret_idx, jitter, spp, seed=0, chain_offset=0, want_cov=False, want_samples=True, ctx=None,
+        dot_offset=0):
     """samples [n_outer, n_chains, stride]; doT scalar or array. Returns dict(mean [D,C,R,n], cov [D,C,R,n,n] or None,
-    samples [D,C,R*spp,n] or None, info [D,C,R])."""
+    samples [D,C,R*spp,n] or None, info [D,C,R]). dot_offset: global index of doT[0] when doT is a slice of a sharded sweep."""
     from .kernel import default_context
     ctx = ctx or default_context()
     _bind(ctx.lib); _bind_est(ctx.lib)
@@ -58,12 +63,17 @@ def ite(samples, X, T, Y, nU, doT, ret_idx, jitter, spp, seed=0, chain_offset=0,
     cov = np.empty((D, C, R, n, n)) if want_cov else None
     smp = np.empty((D, C, R * spp, n)) if (want_samples and spp > 0) else None
     info = np.empty((D, C, R), dtype=np.int32)
-    ctx.check(ctx.lib.gpslc_ite(ctx.h, HOST, ctypes.byref(d), ptr(samples), n_outer, C, stride, ptr(ret), R, ptr(doT), D,
-                                float(jitter), int(spp), int(seed), int(chain_offset), ptr(mean), ptr(cov), ptr(smp), ptr(info)))
+    if dot_offset:
+        ctx.check(ctx.lib.gpslc_ite_slice(ctx.h, HOST, ctypes.byref(d), ptr(samples), n_outer, C, stride, ptr(ret), R, ptr(doT), D,
+                                          int(dot_offset), float(jitter), int(spp), int(seed), int(chain_offset), ptr(mean), ptr(cov),
+                                          ptr(smp), ptr(info)))
+    else:
+        ctx.check(ctx.lib.gpslc_ite(ctx.h, HOST, ctypes.byref(d), ptr(samples), n_outer, C, stride, ptr(ret), R, ptr(doT), D,
+                                    float(jitter), int(spp), int(seed), int(chain_offset), ptr(mean), ptr(cov), ptr(smp), ptr(info)))
     return {"mean": mean, "cov": cov, "samples": smp, "info": info}
 
 
-def sate(samples, X, T, Y, nU, doT, ret_idx, jitter, spp, seed=0, chain_offset=0, var_as_std=True, ctx=None):
+def sate(samples, X, T, Y, nU, doT, ret_idx, jitter, spp, seed=0, chain_offset=0, var_as_std=True, ctx=None, dot_offset=0):
     """Returns dict(mean [D,C,R], var [D,C,R], samples [D,C,R*spp], info)."""
     from .kernel import default_context
     ctx = ctx or default_context()
@@ -75,9 +85,14 @@ def sate(samples, X, T, Y, nU, doT, ret_idx, jitter, spp, seed=0, chain_offset=0
     ret = np.ascontiguousarray(ret_idx, dtype=np.int32)
     D, R = doT.shape[0], ret.shape[0]
     mean = np.empty((D, C, R)); var = np.empty((D, C, R)); smp = np.empty((D, C, R * spp)); info = np.empty((D, C, R), dtype=np.int32)
-    ctx.check(ctx.lib.gpslc_sate(ctx.h, HOST, ctypes.byref(d), ptr(samples), n_outer, C, stride, ptr(ret), R, ptr(doT), D,
-                                 float(jitter), int(spp), int(seed), int(chain_offset), int(bool(var_as_std)), ptr(mean), ptr(var),
-                                 ptr(smp), ptr(info)))
+    if dot_offset:
+        ctx.check(ctx.lib.gpslc_sate_slice(ctx.h, HOST, ctypes.byref(d), ptr(samples), n_outer, C, stride, ptr(ret), R, ptr(doT), D,
+                                           int(dot_offset), float(jitter), int(spp), int(seed), int(chain_offset),
+                                           int(bool(var_as_std)), ptr(mean), ptr(var), ptr(smp), ptr(info)))
+    else:
+        ctx.check(ctx.lib.gpslc_sate(ctx.h, HOST, ctypes.byref(d), ptr(samples), n_outer, C, stride, ptr(ret), R, ptr(doT), D,
+                                     float(jitter), int(spp), int(seed), int(chain_offset), int(bool(var_as_std)), ptr(mean), ptr(var),
+                                     ptr(smp), ptr(info)))
     return {"mean": mean, "var": var, "samples": smp, "info": info}
 
 

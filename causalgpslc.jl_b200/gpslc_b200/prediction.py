@@ -8,13 +8,18 @@ from .estimation import ite as _ite
 from .utils import getN, getNumPosteriorSamples
 
 
-def predictCounterfactualEffects(g, nSamplesPerMixture, fidelity=100, minDoT=None, maxDoT=None, ctx=None):
-    """src/prediction.jl:23-36 -> (ite [d, n, R*nSamplesPerMixture], doTrange)."""
+def predictCounterfactualEffects(g, nSamplesPerMixture, fidelity=100, minDoT=None, maxDoT=None, ctx=None, world_size=1, rank=0):
+    """src/prediction.jl:23-36 -> (ite [d, n, R*nSamplesPerMixture], doTrange).
+    world_size/rank (not in the reference): the doT values are the independent units of the sweep; rank r
+    computes the contiguous block `shard_chains(len(doTrange), world_size, r)` and returns only those rows of `ite` (plus the
+    full range). The draws are keyed by the global doT index, so the shards concatenate to the unsharded result."""
+    from .parallel import shard_chains
     minDoT = float(np.min(g.T)) if minDoT is None else float(minDoT)
     maxDoT = float(np.max(g.T)) if maxDoT is None else float(maxDoT)
     doTrange = np.linspace(minDoT, maxDoT, fidelity + 1)      # minDoT:step:maxDoT, step = |max-min|/fidelity
-    o = _ite(g.posteriorPacked[:, :1], g.X, g.T, g.Y, g.hyperparams.nU, doTrange, _ret(g),
-             g.hyperparams.predictionCovarianceNoise, nSamplesPerMixture, seed=g.seed, ctx=ctx)
-    ite = np.swapaxes(o["samples"][:, 0], 1, 2)               # [d, n, R*spp]
-    assert ite.shape == (len(doTrange), getN(g), getNumPosteriorSamples(g) * nSamplesPerMixture)
+    off, cnt = shard_chains(len(doTrange), world_size, rank)
+    o = _ite(g.posteriorPacked[:, :1], g.X, g.T, g.Y, g.hyperparams.nU, doTrange[off:off + cnt], _ret(g),
+             g.hyperparams.predictionCovarianceNoise, nSamplesPerMixture, seed=g.seed, ctx=ctx, dot_offset=off)
+    ite = np.swapaxes(o["samples"][:, 0], 1, 2)               # [d_local, n, R*spp]
+    assert ite.shape == (cnt, getN(g), getNumPosteriorSamples(g) * nSamplesPerMixture)
     return ite, doTrange

@@ -194,6 +194,21 @@ function predictCounterfactualEffects(g, nSamplesPerMixture::Int; fidelity::Int=
     permutedims(out, (3, 1, 2)), doTrange                           # ite[d, n, R*spp] as the reference returns
 end
 
+"""
+    summarizeEstimates(samples; credible_interval=0.90) — the statistics of src/driver.jl:129-149 (row mean and the two
+quantiles, Julia `quantile` default) through gpslc_summarize. `samples` is the n × m matrix sampleITE returns, whose memory
+is exactly the C layout [m][n]. Returns (Mean, LowerBound, UpperBound) vectors; the DataFrame/CSV part stays in driver.jl.
+"""
+function summarizeEstimates(samples::Matrix{Float64}; credible_interval::Float64=0.90)
+    n, m = size(samples)
+    out = Matrix{Float64}(undef, 3, n)                               # C layout [n][3]
+    GC.@preserve samples out begin
+        check(ccall((:gpslc_summarize, LIB[]), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Cint, Cint, Cint, Cdouble, Ptr{Cdouble}),
+                    CTX[], 0, samples, 1, m, n, credible_interval, out))
+    end
+    out[1, :], out[2, :], out[3, :]
+end
+
 "rbfKernelLog / processCov (src/kernel.jl:24-59) through gpslc_cov_build — parity layer"
 function covBuild(X1::Matrix{Float64}, X2::Matrix{Float64}, LS::Vector{Float64}, scale::Float64, noise::Union{Float64,Nothing}=nothing)
     n, D = size(X1); K = Matrix{Float64}(undef, n, n)

@@ -188,6 +188,17 @@ int gpslc_sate(gpslc_ctx* ctx, int loc, const gpslc_data* data, const double* sa
                const int* ret_idx, int R, const double* doT, int n_doT, double jitter, int spp, uint64_t seed, int chain_offset,
                int var_as_std, double* meanSATE, double* varSATE, double* sate, int* info);
 
+/* gpslc_ite / gpslc_sate for a SLICE of a counterfactual sweep (predictCounterfactualEffects, src/prediction.jl:23-36, sharded
+ * over GPUs — BASELINE config c5: 256 doT values, 32 per GPU): doT[0..n_doT) are elements dot_offset.. of the full sweep. The
+ * draws' Philox streams are keyed by the global doT index, so the slices concatenate to exactly what the unsharded call
+ * returns. All other arguments and outputs as in gpslc_ite / gpslc_sate. */
+int gpslc_ite_slice(gpslc_ctx* ctx, int loc, const gpslc_data* data, const double* samples, int n_outer, int n_chains, int stride,
+                    const int* ret_idx, int R, const double* doT, int n_doT, int dot_offset, double jitter, int spp, uint64_t seed,
+                    int chain_offset, double* meanITE, double* covITE, double* ite, int* info);
+int gpslc_sate_slice(gpslc_ctx* ctx, int loc, const gpslc_data* data, const double* samples, int n_outer, int n_chains, int stride,
+                     const int* ret_idx, int R, const double* doT, int n_doT, int dot_offset, double jitter, int spp, uint64_t seed,
+                     int chain_offset, int var_as_std, double* meanSATE, double* varSATE, double* sate, int* info);
+
 /* summarizeEstimates (src/driver.jl:129-149): for every individual the mean and the (1-ci)/2 and 1-(1-ci)/2 quantiles of its
  * m samples, Julia's default `quantile` (linear interpolation between order statistics, type 7; KAT test/driver.jl:54-71).
  *   samples [batch][m][n]  — the layout gpslc_ite writes (`ite` for one doT and one chain is one batch element with

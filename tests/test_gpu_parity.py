@@ -360,6 +360,19 @@ def test_predict_counterfactual_effects(ctx):
     assert np.all(np.isfinite(ite)) and np.abs(ite[2].mean(axis=1) - M0.mean(axis=0)).max() < 5.0
 
 
+def test_counterfactual_sweep_shards_concatenate(ctx):
+    """The doT values of predictCounterfactualEffects are the units sharded over GPUs (BASELINE config c5): rank-local slices
+    (gpslc_ite_slice, global doT index in the RNG key) must concatenate to exactly the unsharded sweep, draws included."""
+    counts, X, T, Y = od.synthetic(60, 4, 2, seed=12)
+    h = g.getHyperParameters(); h.nOuter, h.nBurnIn = 6, 3
+    gobj = g.gpslc(counts, X, T, Y, hyperparams=h, ctx=ctx)
+    whole, rng_ = g.predictCounterfactualEffects(gobj, 3, fidelity=6, ctx=ctx)
+    for world in (2, 3):
+        parts = [g.predictCounterfactualEffects(gobj, 3, fidelity=6, ctx=ctx, world_size=world, rank=r)[0] for r in range(world)]
+        assert sum(p.shape[0] for p in parts) == 7
+        assert np.array_equal(np.concatenate(parts, axis=0), whole)
+
+
 def test_binary_treatment_end_to_end_ihdp(ctx):
     """IHDP_sampled.csv (n=272, 6 covariates, 200 objects, Bool T): gpslc -> sampleITE(true/false) runs the binary-T
     sampler; the golden files test/test_results/IHDP_sampled_{true,false}.csv have no test in the reference,
