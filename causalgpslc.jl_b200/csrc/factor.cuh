@@ -526,9 +526,11 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                                 double v00, v01, v10, v11;
                                 gen.quad(r, r, c, v00, v01, v10, v11);
                                 const int ri = r - snapJ * NB, ci = c - snapJ * NB;
+                                // diagonal 8x8 tiles are computed in full: only their lower triangle is mirrored, so that every
+                                // element of the snapshot has exactly one writer and the result is exactly symmetric
                                 if (ri < snap_n) {
-                                    if (ci < snap_n) { snap[(size_t)ci * snap_n + ri] = v00 - acc[sl][0]; snap[(size_t)ri * snap_n + ci] = v00 - acc[sl][0]; }
-                                    if (ci + 1 < snap_n) { snap[(size_t)(ci + 1) * snap_n + ri] = v01 - acc[sl][1]; snap[(size_t)ri * snap_n + ci + 1] = v01 - acc[sl][1]; }
+                                    if (ci <= ri) { snap[(size_t)ci * snap_n + ri] = v00 - acc[sl][0]; snap[(size_t)ri * snap_n + ci] = v00 - acc[sl][0]; }
+                                    if (ci + 1 <= ri) { snap[(size_t)(ci + 1) * snap_n + ri] = v01 - acc[sl][1]; snap[(size_t)ri * snap_n + ci + 1] = v01 - acc[sl][1]; }
                                 }
                             }
                         }

@@ -103,6 +103,51 @@ def test_full_size_properties_n1024(ctx):
     assert np.max(np.abs(c[2] - 4 * b_[2]) / b_[2]) <= 1e-12 and np.allclose(c[1], b_[1], rtol=1e-14)
 
 
+def test_full_size_properties_n4096(ctx):
+    """BASELINE c4 size (64 panels per matrix): closed forms and linearity through the fused build + Cholesky."""
+    n, batch = 4096, 2
+    rng = np.random.default_rng(6)
+    y = rng.standard_normal(n)
+    F = rng.standard_normal((n, 11)); sc = np.array([0.7, 1.3]); nz = np.array([0.3, 0.5])
+    lp, ld, q, info = g.rbf_logpdf(F, np.full((batch, 11), 1e9), sc, nz, y, ctx=ctx)
+    assert np.all(info == 0)
+    for b in range(batch):
+        ld_want = (n - 1) * np.log(nz[b]) + np.log(nz[b] + n * sc[b])
+        q_want = (y @ y) / nz[b] - sc[b] * y.sum() ** 2 / (nz[b] * (nz[b] + n * sc[b]))
+        assert abs(ld[b] - ld_want) <= 1e-9 * abs(ld_want) and abs(q[b] - q_want) <= 1e-8 * abs(q_want)
+    ls = 2.0 + 2 * rng.random((batch, 11))
+    b1 = g.rbf_logpdf(F, ls, sc, nz, y, ctx=ctx); b2 = g.rbf_logpdf(F, ls, sc, nz, -3 * y, ctx=ctx)
+    assert np.all(b1[3] == 0) and np.max(np.abs(b2[2] - 9 * b1[2]) / b1[2]) <= 1e-12 and np.allclose(b2[1], b1[1], rtol=1e-14)
+    # permuting the individuals permutes K symmetrically: same determinant and quadratic form (different panel contents)
+    perm = rng.permutation(n)
+    b3 = g.rbf_logpdf(F[perm], ls, sc, nz, y[perm], ctx=ctx)
+    assert np.max(np.abs(b3[1] - b1[1]) / np.abs(b1[1])) <= 1e-10 and np.max(np.abs(b3[2] - b1[2]) / b1[2]) <= 1e-9
+
+
+def test_large_ite_in_team_mode_is_consistent_with_sate(ctx):
+    """n = 2048 (4096 x 4096 augmented matrices, few tasks => cluster teams picked automatically): the SATE fast path (one
+    n x n Cholesky with two right-hand sides, never forms CovITE) must agree with the mean / grand sum of what the ITE path
+    produces, and the zero-effect structure must hold at doT where T == doT for nobody (finite, PD, symmetric CovITE)."""
+    n, n_obj, nX = 2048, 32, 4
+    counts, X, T, Y = od.synthetic(n, n_obj, nX, seed=21)
+    spec = om.ModelSpec(n, 1, nX, False)
+    rng = np.random.default_rng(3)
+    rec = np.ones(spec.n_params + n)
+    rec[:spec.n_params] = 0.8 + 0.4 * rng.random(spec.n_params)
+    rec[2] = 0.3
+    rec[spec.n_params:] = np.repeat(rng.standard_normal(n_obj), n // n_obj)
+    doT = np.array([-0.5, 0.1, 0.9])
+    ret = np.array([0], dtype=np.int32)
+    o = ge.ite(rec[None, None, :], X, T, Y, 1, doT, ret, 1e-10, 2, want_cov=True, ctx=ctx)
+    so = ge.sate(rec[None, None, :], X, T, Y, 1, doT, ret, 1e-10, 2, ctx=ctx)
+    assert o["info"].max() == 0 and so["info"].max() == 0 and np.all(np.isfinite(o["samples"]))
+    for d in range(3):
+        M, Cv = o["mean"][d, 0, 0], o["cov"][d, 0, 0]
+        assert np.array_equal(Cv, Cv.T)
+        assert abs(M.mean() - so["mean"][d, 0, 0]) <= 1e-9 * max(1.0, abs(M).max())
+        assert abs(Cv.sum() / n ** 2 - so["var"][d, 0, 0]) <= 1e-7 * abs(so["var"][d, 0, 0]) + 1e-12
+
+
 # ------------------------------------------------------------------------------------------------ sampler vs oracle chain
 def _run_pair(md, X, T, Y, counts, nOuter, nMH, nES, seed, C, **opts):
     s = ChainSampler(md.prior, X, T, Y, md.spec.nU, counts, nOuter, nMH, nES, n_chains=C, seed=seed, **opts)
