@@ -468,51 +468,58 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
             double wsum[MAXRHS] = {0.0, 0.0};
             double wsnap[MAXRHS] = {0.0, 0.0};  // residual after the leading snapJ panels only (ITE: -MeanITE)
             const int wr = tid >> 2, kq = tid & 3;  // RHS update mapping: row wr, k pair kq
-            // operand slab t of the diagonal block row goes into pipeline slot gi (stage known to be free); the first STAGES
-            // slabs are issued here, the others by the last warp that leaves the stage they reuse
-            auto issue_diag_slab = [&](const int t, const uint32_t gi) {
+            // The diagonal k-loop needs only the block row's own slabs (8 KB each), so a stage carries DS = 2 of them (one 16 KB
+            // bulk copy): half as many barrier rounds per DMMA. Pair t2 goes into pipeline slot gi (stage known to be free); the
+            // first STAGES pairs are issued here, the others by the last warp that leaves the stage they reuse.
+            constexpr int DS = 2;
+            const int T2 = T / DS;      // T = 4 j is a multiple of 4
+            auto issue_diag_slab = [&](const int t2, const uint32_t gi) {
                 const int st = gi % STAGES;
-                mbar_expect_tx(&sm.full[st], SLAB_D * 8);
-                bulk_g2s(sm.stage + st * STAGE_D + 2 * SLAB_D, scratch + row_off(j) + (size_t)t * SLAB_D, SLAB_D * 8, &sm.full[st]);
+                mbar_expect_tx(&sm.full[st], DS * SLAB_D * 8);
+                bulk_g2s(sm.stage + st * STAGE_D + SLAB_D, scratch + row_off(j) + (size_t)t2 * DS * SLAB_D, DS * SLAB_D * 8, &sm.full[st]);
             };
-            for (int t = 0; t < STAGES && t < T; t++) {
-                const uint32_t gi = pipe.consumed + t;
-                if (lane == 0 && warp == (int)(gi & (FWARPS - 1))) issue_diag_slab(t, gi);
+            for (int t2 = 0; t2 < STAGES && t2 < T2; t2++) {
+                const uint32_t gi = pipe.consumed + t2;
+                if (lane == 0 && warp == (int)(gi & (FWARPS - 1))) issue_diag_slab(t2, gi);
             }
             const bool in_tail = SNAP && (j >= snapJ);
             const bool do_snap = in_tail && (snap != nullptr) && (trank == 0);
             const int Tsnap = in_tail ? snapJ * NSLAB : T;
-            auto kloop = [&](const int tb, const int te) {
-                for (int t = tb; t < te; t++) {
+            auto kloop = [&](const int tb, const int te) {     // slab pairs [tb, te)
+                for (int t2 = tb; t2 < te; t2++) {
                     const uint32_t gi = pipe.consumed++;
                     const int st = gi % STAGES;
                     mbar_wait(&sm.full[st], (gi / STAGES) & 1);
-                    const double* sB = sm.stage + st * STAGE_D + 2 * SLAB_D;
 #pragma unroll
-                    for (int k4 = 0; k4 < K4S; k4++) {
+                    for (int kk2 = 0; kk2 < DS; kk2++) {
+                        const double* sB = sm.stage + st * STAGE_D + SLAB_D + kk2 * SLAB_D;
 #pragma unroll
-                        for (int sl = 0; sl < DSLOTS; sl++) {
-                            if (sl < nslots) {
-                                const double a = sB[(srow[sl] * K4S + k4) * 32 + lane];
-                                const double b = sB[(scol[sl] * K4S + k4) * 32 + lane];
-                                dmma(acc[sl], a, b);
+                        for (int k4 = 0; k4 < K4S; k4++) {
+#pragma unroll
+                            for (int sl = 0; sl < DSLOTS; sl++) {
+                                if (sl < nslots) {
+                                    const double a = sB[(srow[sl] * K4S + k4) * 32 + lane];
+                                    const double b = sB[(scol[sl] * K4S + k4) * 32 + lane];
+                                    dmma(acc[sl], a, b);
+                                }
+                            }
+                        }
+                        if (nrhs > 0) {
+                            // row wr of the diagonal block row, k columns kq, kq+4, ... of the slab (one double per 8x4 atom row)
+                            const int t = t2 * DS + kk2;
+#pragma unroll
+                            for (int kk = 0; kk < KB / 4; kk++) {
+                                const int kc = kq + 4 * kk;    // column inside the slab
+                                const double l = sB[(wr >> 3) * (K4S * 32) + (kc >> 2) * 32 + (wr & 7) * 4 + (kc & 3)];
+                                for (int rh = 0; rh < nrhs; rh++) wsum[rh] = fma(l, zbuf[(size_t)rh * npad + t * KB + kc], wsum[rh]);
                             }
                         }
                     }
-                    if (nrhs > 0) {
-                        // row wr of the diagonal block row, k columns kq, kq+4, ... of the slab (one double per 8x4 atom row)
-#pragma unroll
-                        for (int kk = 0; kk < KB / 4; kk++) {
-                            const int kc = kq + 4 * kk;    // column inside the slab
-                            const double l = sB[(wr >> 3) * (K4S * 32) + (kc >> 2) * 32 + (wr & 7) * 4 + (kc & 3)];
-                            for (int rh = 0; rh < nrhs; rh++) wsum[rh] = fma(l, zbuf[(size_t)rh * npad + t * KB + kc], wsum[rh]);
-                        }
-                    }
                     __syncwarp();
-                    if (lane == 0 && stage_release_is_last(&sm.freed[st]) && t + STAGES < T) issue_diag_slab(t + STAGES, gi + STAGES);
+                    if (lane == 0 && stage_release_is_last(&sm.freed[st]) && t2 + STAGES < T2) issue_diag_slab(t2 + STAGES, gi + STAGES);
                 }
             };
-            kloop(0, Tsnap);
+            kloop(0, Tsnap / DS);
             if constexpr (SNAP) {
                 if (in_tail) {
                     wsnap[0] = wsum[0]; wsnap[1] = wsum[1];
@@ -535,7 +542,7 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                             }
                         }
                     }
-                    kloop(Tsnap, T);
+                    kloop(Tsnap / DS, T2);
                 }
             }
             __syncthreads();  // every warp is done with the stage buffers -> P2 may alias them
