@@ -447,8 +447,6 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
     GP_PHASE_INIT();
     for (int j = 0; j < NCB; j++) {
         const int T = j * NSLAB;  // slabs in the k-loop of this panel
-        gen.stage_cols(j * NB, sm.colfeat);
-        __syncthreads();
         // =================================================================== diagonal tile
         {
             // The 36 lower 8x8 tiles of the diagonal block are dealt 5/4 to the warps (instead of w+1 to warp w): warps p and
@@ -482,6 +480,9 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                 const uint32_t gi = pipe.consumed + t2;
                 if (lane == 0 && warp == (int)(gi & (FWARPS - 1))) issue_diag_slab(t2, gi);
             }
+            // column features of this panel for the generators, while the first operand copies are in flight; they are first
+            // read after the barrier that follows the k-loop, and the previous panel's readers are behind its end-of-panel barrier
+            gen.stage_cols(j * NB, sm.colfeat);
             const bool in_tail = SNAP && (j >= snapJ);
             const bool do_snap = in_tail && (snap != nullptr) && (trank == 0);
             const int Tsnap = in_tail ? snapJ * NSLAB : T;
@@ -593,13 +594,12 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                     if (!in_tail) zbuf[(size_t)(MAXRHS + rh) * npad + j * NB + r] = sm.wvec[rh][r];
                 }
             }
-            __syncthreads();
             if (tid < NB && nrhs > 0) {
-                // gram sums: read back z from global (just written by this CTA; visible after the barrier)
-                const double z0 = zbuf[j * NB + tid];
+                // gram sums straight from the bordered rows of Cs
+                const double z0 = Cs[NB * CS_LD + tid];
                 sm.part[1][tid] = fma(z0, z0, sm.part[1][tid]);
                 if (nrhs > 1) {
-                    const double z1 = zbuf[(size_t)npad + j * NB + tid];
+                    const double z1 = Cs[(NB + 1) * CS_LD + tid];
                     sm.part[2][tid] = fma(z0, z1, sm.part[2][tid]);
                     sm.part[3][tid] = fma(z1, z1, sm.part[3][tid]);
                 }
