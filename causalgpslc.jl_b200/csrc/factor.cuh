@@ -60,6 +60,7 @@ struct __align__(128) FactorSmem {
     double linv[LINV_D];               // 18 KB; inverse of the current diagonal block: the 72 8x4 atoms on/below the diagonal
     double colfeat[CF_DIMS * NB];      // 12 KB; feature values of the current panel's 64 columns (covariance generation)
     double exp2tab[32];                // 2^(i/32) for the generators' exponential; must directly follow colfeat
+    double p2buf[72];                  // pivot-warp broadcast buffer: an 8x8 column block of L and the 8 reciprocal pivots
     double wvec[MAXRHS][NB];           // w_j (pre-solve) / scratch
     double part[4][NB];                // per-row partial sums: log L_ii, z0.z0, z0.z1, z1.z1 (kept out of registers)
     double* snap; int snapJ, snap_n;   // snapshot hook parameters
@@ -216,11 +217,22 @@ __device__ inline void p2_factor_diag(FactorSmem& sm, double* Cs, int col0) {
 #endif
 #pragma unroll
         for (int k = 0; k < 8; k++) a[k] = (k <= r) ? Cs[(c0 + r) * CS_LD + c0 + k] : 0.0;
-        double rinv_r = 0.0;
         GP_SUB(16);
+        // Column k of L and 1/L_kk are broadcast through a 72-double shared-memory buffer (one 8-byte store per lane, then
+        // 16-byte broadcast loads of column pairs) instead of one 2-instruction shuffle per element: the serial warp's time is
+        // proportional to its instruction count (about one instruction per 6 cycles, measured), and shuffles were half of it.
+        double* colbuf = sm.p2buf;          // [k][j] = L[j][k]
+        double* rinvbuf = sm.p2buf + 64;    // [k] = 1 / L[k][k]
+        double Lc[8][8];                    // register copy of the columns (j > k) for the inverse below
+        // The pivot recurrence itself stays off both the shuffles and the buffer: every lane computes the next pivot,
+        //   a_{k+1,k+1} <- a_{k+1,k+1} - (a_{k+1,k} / sqrt(a_kk))^2,
+        // from two values of lane k+1 that are broadcast BEFORE 1/sqrt(a_kk) is known (the same expression, bit for bit, that lane
+        // k+1 evaluates in its own update), so the serial chain per pivot is rsqrt -> mul -> fma.
+        double akk = __shfl_sync(FULL, a[0], 0);
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            double akk = __shfl_sync(FULL, a[k], k);
+            double d10 = 0.0, d11 = 0.0;
+            if (k < 7) { d10 = __shfl_sync(FULL, a[k], k + 1); d11 = __shfl_sync(FULL, a[k + 1], k + 1); }
             // positive and finite? (integer test on the high word: no FP64-pipe instruction; NaN and denormal pivots fail it)
             const int hik = __double2hiint(akk);
             if (!(hik > 0 && hik < 0x7ff00000)) {
@@ -228,27 +240,33 @@ __device__ inline void p2_factor_diag(FactorSmem& sm, double* Cs, int col0) {
                 akk = 1.0;
             }
             const double ri = rsqrt_fast(akk);
+            const double l10 = d10 * ri;
+            akk = fma(-l10, l10, d11);          // next pivot
             const double lk = a[k] * ri;
             a[k] = lk;
-            if (r == k) rinv_r = ri;
+            if (lane < 8) colbuf[k * 8 + r] = lk;
+            if (lane == k) rinvbuf[k] = ri;
+            __syncwarp();
+            if (k < 7) {
 #pragma unroll
-            for (int j = k + 1; j < 8; j++) {
-                const double ljk = __shfl_sync(FULL, lk, j);
-                a[j] = fma(-lk, ljk, a[j]);
+                for (int jj = (k + 1) & ~1; jj < 8; jj += 2) {
+                    const double2 lp = *reinterpret_cast<const double2*>(colbuf + k * 8 + jj);
+                    if (jj > k) { Lc[k][jj] = lp.x; a[jj] = fma(-lk, lp.x, a[jj]); }
+                    Lc[k][jj + 1] = lp.y; a[jj + 1] = fma(-lk, lp.y, a[jj + 1]);
+                }
             }
         }
         GP_SUB(17);
-        double x[8];
+        // inverse, lane r owns column r of X = L^-1; right-looking, so the dependent chain is one fma and one mul per row
+        double x[8], sacc[8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const double rii = __shfl_sync(FULL, rinv_r, i);
-            double s = 0.0;
+        for (int i = 0; i < 8; i++) sacc[i] = 0.0;
 #pragma unroll
-            for (int k = 0; k < i; k++) {
-                const double lik = __shfl_sync(FULL, a[k], i);
-                s = fma(lik, x[k], s);
-            }
-            x[i] = (i == r) ? rii : ((i > r) ? -s * rii : 0.0);
+        for (int k = 0; k < 8; k++) {
+            const double rkk = rinvbuf[k];
+            x[k] = (k == r) ? rkk : ((k > r) ? -sacc[k] * rkk : 0.0);
+#pragma unroll
+            for (int i = k + 1; i < 8; i++) sacc[i] = fma(Lc[k][i], x[k], sacc[i]);
         }
         GP_SUB(18);
         if (lane < 8) {
