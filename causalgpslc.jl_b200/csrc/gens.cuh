@@ -135,27 +135,42 @@ struct RbfGen {
             for (int ni = 0; ni < NI; ni++) { a[0][ni][0] = 0.0; a[0][ni][1] = 0.0; a[1][ni][0] = 0.0; a[1][ni][1] = 0.0; }
             const int D = s->D;
             const bool staged = GPSLC_STAGE_COLS && (D <= CF_DIMS);
+            // two separate loops (not one loop with a branch inside): ptxas if-converted the inner branch and executed the
+            // global loads and multiplies of the unstaged path speculatively on every iteration
+            if (staged) {
 #pragma unroll 4
-            for (int d = 0; d < D; d++) {
-                const double* p = s->feat[d];
-                const double w = s->sw[d];
-                const double z0 = __ldg(p + r0) * w;
-                const double z1 = ONE_ROW ? z0 : __ldg(p + r1) * w;
+                for (int d = 0; d < D; d++) {
+                    const double w = s->sw[d];
+                    const double z0 = __ldg(s->feat[d] + r0) * w;
+                    const double z1 = ONE_ROW ? z0 : __ldg(s->feat[d] + r1) * w;
 #pragma unroll
-                for (int ni = 0; ni < NI; ni++) {
-                    double c0v, c1v;
-                    if (staged) {
+                    for (int ni = 0; ni < NI; ni++) {
                         const double2 cc = *reinterpret_cast<const double2*>(cf + d * NB + cl + 8 * ni);
-                        c0v = cc.x; c1v = cc.y;
-                    } else {
-                        c0v = __ldg(p + c0 + 8 * ni) * w; c1v = __ldg(p + c0 + 8 * ni + 1) * w;
+                        double t;
+                        t = z0 - cc.x; a[0][ni][0] = fma(t, t, a[0][ni][0]);
+                        t = z0 - cc.y; a[0][ni][1] = fma(t, t, a[0][ni][1]);
+                        if (!ONE_ROW) {
+                            t = z1 - cc.x; a[1][ni][0] = fma(t, t, a[1][ni][0]);
+                            t = z1 - cc.y; a[1][ni][1] = fma(t, t, a[1][ni][1]);
+                        }
                     }
-                    double t;
-                    t = z0 - c0v; a[0][ni][0] = fma(t, t, a[0][ni][0]);
-                    t = z0 - c1v; a[0][ni][1] = fma(t, t, a[0][ni][1]);
-                    if (!ONE_ROW) {
-                        t = z1 - c0v; a[1][ni][0] = fma(t, t, a[1][ni][0]);
-                        t = z1 - c1v; a[1][ni][1] = fma(t, t, a[1][ni][1]);
+                }
+            } else {
+                for (int d = 0; d < D; d++) {
+                    const double* p = s->feat[d];
+                    const double w = s->sw[d];
+                    const double z0 = __ldg(p + r0) * w;
+                    const double z1 = ONE_ROW ? z0 : __ldg(p + r1) * w;
+#pragma unroll
+                    for (int ni = 0; ni < NI; ni++) {
+                        const double c0v = __ldg(p + c0 + 8 * ni) * w, c1v = __ldg(p + c0 + 8 * ni + 1) * w;
+                        double t;
+                        t = z0 - c0v; a[0][ni][0] = fma(t, t, a[0][ni][0]);
+                        t = z0 - c1v; a[0][ni][1] = fma(t, t, a[0][ni][1]);
+                        if (!ONE_ROW) {
+                            t = z1 - c0v; a[1][ni][0] = fma(t, t, a[1][ni][0]);
+                            t = z1 - c1v; a[1][ni][1] = fma(t, t, a[1][ni][1]);
+                        }
                     }
                 }
             }

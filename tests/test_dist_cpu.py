@@ -32,6 +32,12 @@ def _worker(rank, world, port, q):
         for c in range(nloc):
             local[i, c] = 100 * i + 10 * (off + c) + np.arange(4)
     full = gather_chain_axis(local, total, axis=1)
+    # counterfactual sweep: the doT values are the sharded units, the [doT, n, 3] summaries are gathered along axis 0
+    n_dot = 7
+    doff, dcnt = shard_chains(n_dot, world, rank)
+    summ = np.stack([np.full((6, 3), float(doff + d)) for d in range(dcnt)]) if dcnt else np.zeros((0, 6, 3))
+    allsum = gather_chain_axis(summ, n_dot, axis=0)
+    assert allsum.shape == (n_dot, 6, 3) and np.array_equal(allsum[:, 0, 0], np.arange(n_dot, dtype=float))
     q.put((rank, full))
     dist.barrier()
     dist.destroy_process_group()

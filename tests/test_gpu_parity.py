@@ -261,6 +261,23 @@ def test_error_behaviour(ctx):
     s.close()
 
 
+def test_empty_inputs_are_no_ops(ctx):
+    """Zero retained samples, zero interventions, zero batch elements: success and empty outputs, no launch, no fault."""
+    counts, X, T, Y = od.synthetic(24, 2, 2, seed=2)
+    md = od.model_data_from_arrays(counts, X, T, Y, nU=1)
+    smp = oi.posterior(md, 2, 1, 1, seed=1, chain=0, observe_x=True)[0][:, None, :]
+    o = ge.ite(smp, X, T, Y, 1, np.zeros(0), np.array([0], dtype=np.int32), 1e-10, 3, ctx=ctx)
+    assert o["mean"].shape == (0, 1, 1, 24) and o["samples"].shape == (0, 1, 3, 24)
+    o = ge.ite(smp, X, T, Y, 1, [0.5], np.zeros(0, dtype=np.int32), 1e-10, 3, ctx=ctx)
+    assert o["mean"].shape == (1, 1, 0, 24) and o["info"].size == 0
+    so = ge.sate(smp, X, T, Y, 1, np.zeros(0), np.array([1], dtype=np.int32), 1e-10, 2, ctx=ctx)
+    assert so["samples"].shape == (0, 1, 2)
+    assert ge.summarize(np.zeros((0, 5, 7)), 0.9, ctx=ctx).shape == (0, 7, 3)
+    # spp = 0: distributions only
+    o = ge.ite(smp, X, T, Y, 1, [0.5], np.array([1], dtype=np.int32), 1e-10, 0, ctx=ctx)
+    assert o["samples"] is None and np.all(np.isfinite(o["mean"])) and o["info"].max() == 0
+
+
 # ------------------------------------------------------------------------------------------------ ITE / SATE
 @pytest.mark.parametrize("n,n_obj,nX,nU,with_u", [(40, 4, 3, 1, True), (100, 5, 2, 2, True), (150, 6, 0, 1, True),
                                                   (64, 4, 3, 1, False), (70, 5, 0, 1, False), (300, 6, 4, 1, True)])
