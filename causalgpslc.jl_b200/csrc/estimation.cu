@@ -22,51 +22,58 @@ namespace gpslc {
 struct IteSpec {
     const double* feat[DMAX];   // U columns (record, column-wise as extractParameters builds them) then X columns
     double w[DMAX];
+    double sw[DMAX];            // 1 / lengthscale: the tile generator works on pre-scaled features (see RbfGen)
     const double* T;
     const double* Y;
-    double wT, doT, yScale, yNoise, jitter;
+    double wT, swT, doT, yScale, yNoise, jitter;
     int D, n, npad;
 };
 
+// The strip() fast path and the element-wise one() (ragged edges, snapshot of diagonal tiles) must give bit-identical values for
+// the same entry: which of the two evaluates an entry depends on how the row blocks are tiled (one CTA vs cluster teams), and the
+// results are required not to. Both therefore go through the helpers below, written with explicit round-to-nearest intrinsics so
+// that the compiler cannot contract a multiply-add in one path and not in the other.
 struct IteGen {
     const IteSpec* s;
-    __device__ __forceinline__ double base(int i, int j) const {
-        double a = 0.0;
-        for (int d = 0; d < s->D; d++) {
-            const double* p = s->feat[d];
-            const double t = p[i] - p[j];
-            a = fma(t * s->w[d], t, a);
-        }
-        return a;
+    const double* tab;          // FactorSmem::exp2tab
+    // exp(-(t - doT)^2 / tyLS^2)
+    __device__ __forceinline__ double a_of(double t) const {
+        const double d = __dsub_rn(t, s->doT);
+        return exp_neg_tab(__dmul_rn(__dmul_rn(d, s->wT), d), tab);
+    }
+    // entry value from the shared-dimension distance b, the scaled treatments tis/tjs, and a_i, a_j
+    __device__ __forceinline__ double entry(double b, double tis, double tjs, double ai, double aj, bool r2, bool c2, bool on_diag) const {
+        const double dt = __dsub_rn(tis, tjs);
+        const double eij = exp_neg_tab(__dmul_rn(dt, dt), tab);
+        double gfac;
+        if (!r2) gfac = eij;                                                     // Kp
+        else if (!c2) gfac = __dsub_rn(aj, eij);                                 // D'[i][j] = Kws[j][i] - Kww[j][i]
+        else gfac = __dadd_rn(__dsub_rn(__dsub_rn(eij, ai), aj), 1.0);           // P
+        double val = __dmul_rn(__dmul_rn(s->yScale, exp_neg_tab(b, tab)), gfac);
+        if (on_diag) val = __dadd_rn(val, c2 ? s->jitter : s->yNoise);
+        return val;
     }
     __device__ __forceinline__ double one(int r, int c) const {
         const int n = s->n, np = s->npad;
         const bool r2 = r >= np, c2 = c >= np;
         const int i = r2 ? r - np : r, j = c2 ? c - np : c;
         if (i >= n || j >= n) return (r == c) ? 1.0 : 0.0;
-        const double b = base(i, j);
-        const double ti = s->T[i], tj = s->T[j];
-        const double dt = ti - tj, tt = dt * s->wT * dt;
-        // same factored form as strip(): yScale * exp(-b) * g
-        const double eb = s->yScale * exp_neg(b), eij = exp_neg(tt);
-        if (!r2) {  // Kp
-            double v = eb * eij;
-            if (i == j) v += s->yNoise;
-            return v;
+        double b = 0.0;
+        for (int d = 0; d < s->D; d++) {
+            const double* p = s->feat[d];
+            const double t = __dsub_rn(__dmul_rn(p[i], s->sw[d]), __dmul_rn(p[j], s->sw[d]));
+            b = __fma_rn(t, t, b);
         }
-        const double di = ti - s->doT, dj = tj - s->doT;
-        const double aj = exp_neg(dj * s->wT * dj);
-        if (!c2) return eb * (aj - eij);   // D'[i][j] = Kws[j][i] - Kww[j][i]
-        const double ai = exp_neg(di * s->wT * di);
-        double v = eb * (((eij - ai) - aj) + 1.0);   // P + jitter I
-        if (i == j) v += s->jitter;
-        return v;
+        const double ti = s->T[i], tj = s->T[j];
+        const double ai = (r2 && c2) ? a_of(ti) : 0.0, aj = r2 ? a_of(tj) : 0.0;
+        return entry(b, __dmul_rn(ti, s->swT), __dmul_rn(tj, s->swT), ai, aj, r2, c2, r == c);
     }
     __device__ __forceinline__ void quad(int r0, int r1, int c, double& v00, double& v01, double& v10, double& v11) const {
         v00 = one(r0, c); v01 = one(r0, c + 1); v10 = one(r1, c); v11 = one(r1, c + 1);
     }
     __device__ __forceinline__ double rhs(int which, int r) const { return (r < s->n) ? s->Y[r] : 0.0; }
-    // Column features of the panel (zero beyond n): the D shared dimensions, then T_j, then a_j = exp(-(T_j - doT)^2 / tyLS^2).
+    // Column features of the panel (zero beyond n): the D shared dimensions and T_j, all pre-scaled by 1 / lengthscale, then
+    // a_j = exp(-(T_j - doT)^2 / tyLS^2).
     __device__ __forceinline__ void stage_cols(int col0, double* cf) const {
         const int D = s->D;
         if (D + 2 > CF_DIMS) return;
@@ -75,10 +82,10 @@ struct IteGen {
             const int d = i >> 6, c = j0 + (i & 63);
             double v = 0.0;
             if (c < s->n) {
-                if (d < D) v = __ldg(s->feat[d] + c);
+                if (d < D) v = __dmul_rn(__ldg(s->feat[d] + c), s->sw[d]);
                 else {
                     v = __ldg(s->T + c);
-                    if (d == D + 1) { const double dj = v - s->doT; v = exp_neg(dj * s->wT * dj); }
+                    v = (d == D + 1) ? a_of(v) : __dmul_rn(v, s->swT);
                 }
             }
             cf[i] = v;
@@ -100,50 +107,36 @@ struct IteGen {
 #pragma unroll 4
             for (int d = 0; d < D; d++) {
                 const double* p = s->feat[d];
-                const double w = s->w[d];
-                const double z0 = __ldg(p + i0);
-                const double z1 = ONE_ROW ? z0 : __ldg(p + i1);
+                const double w = s->sw[d];
+                const double z0 = __dmul_rn(__ldg(p + i0), w);
+                const double z1 = ONE_ROW ? z0 : __dmul_rn(__ldg(p + i1), w);
 #pragma unroll
                 for (int ni = 0; ni < NI; ni++) {
                     const double2 cc = *reinterpret_cast<const double2*>(cf + d * NB + cl + 8 * ni);
                     double t;
-                    t = z0 - cc.x; a[0][ni][0] = fma(t * w, t, a[0][ni][0]);
-                    t = z0 - cc.y; a[0][ni][1] = fma(t * w, t, a[0][ni][1]);
+                    t = __dsub_rn(z0, cc.x); a[0][ni][0] = __fma_rn(t, t, a[0][ni][0]);
+                    t = __dsub_rn(z0, cc.y); a[0][ni][1] = __fma_rn(t, t, a[0][ni][1]);
                     if (!ONE_ROW) {
-                        t = z1 - cc.x; a[1][ni][0] = fma(t * w, t, a[1][ni][0]);
-                        t = z1 - cc.y; a[1][ni][1] = fma(t * w, t, a[1][ni][1]);
+                        t = __dsub_rn(z1, cc.x); a[1][ni][0] = __fma_rn(t, t, a[1][ni][0]);
+                        t = __dsub_rn(z1, cc.y); a[1][ni][1] = __fma_rn(t, t, a[1][ni][1]);
                     }
                 }
             }
-            const double sc = s->yScale, wT = s->wT;
             const double t0 = __ldg(s->T + i0), t1 = ONE_ROW ? t0 : __ldg(s->T + i1);
+            const double t0s = __dmul_rn(t0, s->swT), t1s = __dmul_rn(t1, s->swT);
             double ai0 = 0.0, ai1 = 0.0;
-            if (r2 && c2) {
-                const double d0 = t0 - s->doT, d1 = t1 - s->doT;
-                ai0 = exp_neg(d0 * wT * d0); ai1 = ONE_ROW ? ai0 : exp_neg(d1 * wT * d1);
-            }
-            const double diag = c2 ? s->jitter : s->yNoise;
+            if (r2 && c2) { ai0 = a_of(t0); ai1 = ONE_ROW ? ai0 : a_of(t1); }
 #pragma unroll
             for (int ni = 0; ni < NI; ni++) {
                 const double2 tc = *reinterpret_cast<const double2*>(cf + D * NB + cl + 8 * ni);
                 const double2 ac = *reinterpret_cast<const double2*>(cf + (D + 1) * NB + cl + 8 * ni);
 #pragma unroll
                 for (int rr = 0; rr < (ONE_ROW ? 1 : 2); rr++) {
-                    const double ti = rr ? t1 : t0, ai = rr ? ai1 : ai0;
                     const int r = rr ? r1 : r0;
 #pragma unroll
-                    for (int e = 0; e < 2; e++) {
-                        const double tj = e ? tc.y : tc.x, aj = e ? ac.y : ac.x;
-                        const double dt = ti - tj;
-                        const double eij = exp_neg(dt * wT * dt);
-                        double gfac;
-                        if (!r2) gfac = eij;
-                        else if (!c2) gfac = aj - eij;
-                        else gfac = ((eij - ai) - aj) + 1.0;
-                        double val = sc * exp_neg(a[rr][ni][e]) * gfac;
-                        if (r == c0 + 8 * ni + e && r2 == c2) val += diag;
-                        v[rr][ni][e] = val;
-                    }
+                    for (int e = 0; e < 2; e++)
+                        v[rr][ni][e] = entry(a[rr][ni][e], rr ? t1s : t0s, e ? tc.y : tc.x, rr ? ai1 : ai0, e ? ac.y : ac.x, r2, c2,
+                                             r == c0 + 8 * ni + e);
                 }
             }
         } else {
@@ -162,19 +155,19 @@ __device__ inline void fill_ite_spec(const EstArgs& a, const double* rec, double
         if (d < nU) {
             sp->feat[d] = rec + a.n_params + (size_t)d * a.n;
             const double ls = rec[6 + 4 * nX + nU + d];           // uyLS
-            sp->w[d] = 1.0 / (ls * ls);
+            sp->w[d] = 1.0 / (ls * ls); sp->sw[d] = 1.0 / ls;
         } else {
             const int k = d - nU;
             sp->feat[d] = a.X + (size_t)k * a.n;
             const double ls = rec[6 + 3 * nX + k];                // xyLS
-            sp->w[d] = 1.0 / (ls * ls);
+            sp->w[d] = 1.0 / (ls * ls); sp->sw[d] = 1.0 / ls;
         }
     }
     if (threadIdx.x == 0) {
         sp->D = nU + nX; sp->n = a.n; sp->npad = ceil_div(a.n, NB) * NB;
         sp->T = a.T; sp->Y = a.Y;
         const double tyLS = rec[3];
-        sp->wT = 1.0 / (tyLS * tyLS);
+        sp->wT = 1.0 / (tyLS * tyLS); sp->swT = 1.0 / tyLS;
         sp->doT = doT; sp->yNoise = rec[2]; sp->yScale = rec[5]; sp->jitter = a.jitter;
     }
 }
@@ -212,7 +205,7 @@ ite_kernel(EstArgs a, double* scratch, size_t slot_scratch, double* zbuf, size_t
         const double* rec = a.samples + ((size_t)a.ret_idx[r] * a.n_chains + c) * a.stride;
         fill_ite_spec(a, rec, a.doT[d], &spec);
         __syncthreads();
-        IteGen gen{&spec};
+        IteGen gen{&spec, sm.exp2tab};
         double* cov = a.cov_out ? a.cov_out + (size_t)t * a.n * a.n : nullptr;
         factor_run<IteGen, TEAM, true>(gen, NCB, NCB, 1, my_scratch, my_z, sm, pipe, NCB1, cov, a.n);
         const int info = sm.out.info;

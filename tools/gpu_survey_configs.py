@@ -42,4 +42,4 @@ print(f"c3: sampleITE over 64 chains x 1 retained sample x 10 draws: {dt:.3f} s 
 out["c3"]["ite_64x1_s"] = dt
 s.close()
 s, _ = sweep_time("c4", 4096, 64, 10, 64, reps=1); s.close()
-json.dump(out, open(os.path.join(root, "gpurun_out", "configs_r01b.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(root, "gpurun_out", "configs_r01c.json"), "w"), indent=1)
