@@ -53,6 +53,7 @@ void gpslc_destroy(gpslc_ctx* h) {
     if (h->c.scratch) cudaFree(h->c.scratch);
     if (h->c.zbuf) cudaFree(h->c.zbuf);
     if (h->c.counter) cudaFree(h->c.counter);
+    if (h->c.arena) cudaFree(h->c.arena);
     cudaStreamDestroy(h->c.stream);
     delete h;
 }
@@ -101,6 +102,7 @@ int gpslc_cov_build(gpslc_ctx* h, int loc, int n, int batch, int D, const double
     if (!scale) return ctx->fail(GPSLC_ERR_ARG, "gpslc_cov_build: null scale");
     GP_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t nf = (size_t)(feat_shared ? 1 : batch) * D * n;
+    ArenaScope arena_scope(ctx);
     Staged<double> df1(ctx), df2(ctx), dls(ctx), dsc(ctx), dnz(ctx), dK(ctx), dw(ctx);
     GP_TRY(df1.in(loc, f1, nf));
     if (f2 == f1) { df2.d = df1.d; } else GP_TRY(df2.in(loc, f2, nf));
@@ -128,6 +130,7 @@ int gpslc_chol_logpdf(gpslc_ctx* h, int loc, int n, int batch, const double* K, 
     if (n <= 0 || batch < 0 || ld < n || !K || !y) return ctx->fail(GPSLC_ERR_ARG, "gpslc_chol_logpdf: bad argument");
     if (batch == 0) return GPSLC_OK;
     GP_CUDA(ctx, cudaSetDevice(ctx->device));
+    ArenaScope arena_scope(ctx);
     Staged<double> dK(ctx), dy(ctx), dlp(ctx), dld(ctx), dq(ctx);
     Staged<int> dinfo(ctx);
     GP_TRY(dK.in(loc, K, (size_t)batch * ld * n));
@@ -151,6 +154,7 @@ int gpslc_rbf_logpdf(gpslc_ctx* h, int loc, int n, int batch, int D, const doubl
         return ctx->fail(GPSLC_ERR_ARG, "gpslc_rbf_logpdf: bad argument");
     if (batch == 0) return GPSLC_OK;
     GP_CUDA(ctx, cudaSetDevice(ctx->device));
+    ArenaScope arena_scope(ctx);
     Staged<double> df(ctx), dls(ctx), dsc(ctx), dnz(ctx), dy(ctx), dlp(ctx), dld(ctx), dq(ctx);
     Staged<int> dinfo(ctx);
     GP_TRY(df.in(loc, feat, (size_t)(feat_shared ? 1 : batch) * D * n));
@@ -332,6 +336,7 @@ static int est_common(gpslc_ctx* h, int loc, const gpslc_data* d, const double* 
     // ret_idx / doT are tiny host arrays in either mode
     for (int r = 0; r < R; r++)
         if (ret_idx[r] < 0 || ret_idx[r] >= n_outer) return ctx->fail(GPSLC_ERR_ARG, "gpslc_ite/sate: retained index out of range");
+    ArenaScope arena_scope(ctx);
     Staged<double> dX(ctx), dT(ctx), dY(ctx), dS(ctx), dDo(ctx), d1(ctx), d2(ctx), d3(ctx);
     Staged<int> dRet(ctx), dInfo(ctx);
     GP_TRY(dX.in(loc, d->X, (size_t)n * nX));
@@ -396,6 +401,7 @@ int gpslc_summarize(gpslc_ctx* h, int loc, const double* samples, int batch, int
         return ctx->fail(GPSLC_ERR_ARG, "gpslc_summarize: bad argument");
     if (batch == 0) return GPSLC_OK;
     GP_CUDA(ctx, cudaSetDevice(ctx->device));
+    ArenaScope arena_scope(ctx);
     Staged<double> dS(ctx), dO(ctx);
     GP_TRY(dS.in(loc, samples, (size_t)batch * m * n));
     GP_TRY(dO.outbuf(loc, out, (size_t)batch * n * 3));

@@ -10,14 +10,14 @@ template <class T>
 struct Staged {
     Ctx* ctx; T* d = nullptr; T* host = nullptr; size_t count = 0; bool owned = false; bool out = false;
     Staged(Ctx* c) : ctx(c) {}
-    ~Staged() { if (owned && d) cudaFree(d); }
+    ~Staged() {}   // device copies live in the context's staging arena (ArenaScope of the enclosing call)
     // input buffer
     int in(int loc, const T* p, size_t n) {
         count = n;
         if (!p || n == 0) { d = nullptr; return GPSLC_OK; }
         if (loc == 1) { d = const_cast<T*>(p); return GPSLC_OK; }
         owned = true;
-        GP_CUDA(ctx, cudaMalloc(&d, n * sizeof(T)));
+        GP_CUDA(ctx, ctx->arena_alloc(reinterpret_cast<void**>(&d), n * sizeof(T)));
         GP_CUDA(ctx, cudaMemcpyAsync(d, p, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
         return GPSLC_OK;
     }
@@ -27,7 +27,7 @@ struct Staged {
         if (!p || n == 0) { d = nullptr; return GPSLC_OK; }
         if (loc == 1) { d = p; return GPSLC_OK; }
         owned = true; host = p;
-        GP_CUDA(ctx, cudaMalloc(&d, n * sizeof(T)));
+        GP_CUDA(ctx, ctx->arena_alloc(reinterpret_cast<void**>(&d), n * sizeof(T)));
         return GPSLC_OK;
     }
     int finish() {

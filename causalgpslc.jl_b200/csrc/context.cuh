@@ -21,12 +21,47 @@ struct Ctx {
     double* zbuf = nullptr;
     unsigned int* counter = nullptr;  // work-queue counters (device)
     unsigned long long launches = 0;  // kernels launched by this context (bench.py reports it)
+    // Staging arena for host-buffer calls: a bump allocator that is reset at the start of every C-ABI call and grows to the
+    // peak demand seen so far (up to ARENA_MAX), so a steady stream of calls does no cudaMalloc / cudaFree at all (cudaFree
+    // synchronises the device). Requests that do not fit are served by cudaMalloc and freed when the call returns.
+    static constexpr size_t ARENA_MAX = (size_t)1 << 30;
+    char* arena = nullptr;
+    size_t arena_cap = 0, arena_off = 0, arena_peak = 0;
+    std::vector<void*> arena_overflow;
+    void arena_begin() {
+        if (arena_peak > arena_cap && arena_cap < ARENA_MAX) {
+            size_t want = arena_peak < ARENA_MAX ? arena_peak : ARENA_MAX;
+            if (arena) cudaFree(arena);
+            arena = nullptr; arena_cap = 0;
+            if (cudaMalloc(&arena, want) == cudaSuccess) arena_cap = want; else { arena = nullptr; cudaGetLastError(); }
+        }
+        arena_off = 0; arena_peak = 0;
+    }
+    void arena_end() {
+        for (void* p : arena_overflow) cudaFree(p);
+        arena_overflow.clear();
+    }
+    cudaError_t arena_alloc(void** p, size_t bytes) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        arena_peak += bytes;
+        if (arena_off + bytes <= arena_cap) { *p = arena + arena_off; arena_off += bytes; return cudaSuccess; }
+        cudaError_t e = cudaMalloc(p, bytes);
+        if (e == cudaSuccess) arena_overflow.push_back(*p);
+        return e;
+    }
 
     int fail(int code, const std::string& msg) { last_error = msg; return code; }
     int cuda_fail(cudaError_t e, const char* where) {
         last_error = std::string(where) + ": " + cudaGetErrorString(e);
         return GPSLC_ERR_CUDA;
     }
+};
+
+// brackets one C-ABI call: resets the staging arena on entry, releases overflow allocations on exit
+struct ArenaScope {
+    Ctx* c;
+    explicit ArenaScope(Ctx* ctx) : c(ctx) { c->arena_begin(); }
+    ~ArenaScope() { c->arena_end(); }
 };
 
 #define GP_CUDA(ctx, call)                                                   \

@@ -379,7 +379,7 @@ int launch_ite(Ctx* ctx, const EstArgs& a) {
     cudaError_t e = cudaSuccess;
     if (team == 1) {
         GP_CUDA(ctx, cudaFuncSetAttribute(ite_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
-        GP_CUDA(ctx, cudaMalloc(&xi, (size_t)grid * 4 * a.n * sizeof(double)));
+        GP_CUDA(ctx, ctx->arena_alloc(reinterpret_cast<void**>(&xi), (size_t)grid * 4 * a.n * sizeof(double)));
         ite_kernel<0><<<grid, FTHREADS, sizeof(FactorSmem), ctx->stream>>>(a, ctx->scratch, ctx->slot_scratch_d, ctx->zbuf, ctx->slot_z_d, xi,
                                                                          ctx->counter);
         e = cudaGetLastError();
@@ -397,12 +397,11 @@ int launch_ite(Ctx* ctx, const EstArgs& a) {
         if (max_clusters < 1) return ctx->fail(GPSLC_ERR_CUDA, "ite_kernel: no resident cluster of the requested size");
         if (grid > max_clusters) grid = max_clusters;   // fewer teams than slots: the teams loop over the tasks
         cfg.gridDim = dim3(grid * team);
-        GP_CUDA(ctx, cudaMalloc(&xi, (size_t)grid * team * 4 * a.n * sizeof(double)));
+        GP_CUDA(ctx, ctx->arena_alloc(reinterpret_cast<void**>(&xi), (size_t)grid * team * 4 * a.n * sizeof(double)));
         e = cudaLaunchKernelEx(&cfg, ite_kernel<1>, a, ctx->scratch, ctx->slot_scratch_d, ctx->zbuf, ctx->slot_z_d, xi, ctx->counter);
     }
     ctx->launches++;
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
-    cudaFree(xi);
     if (e != cudaSuccess) return ctx->cuda_fail(e, "ite_kernel");
     if (e2 != cudaSuccess) return ctx->cuda_fail(e2, "ite_kernel");
     return GPSLC_OK;
@@ -417,12 +416,11 @@ int launch_sate(Ctx* ctx, const EstArgs& a) {
     const long long total = (long long)a.n_doT * a.n_chains * a.R;
     if (total == 0) return GPSLC_OK;
     double* d1 = nullptr;
-    GP_CUDA(ctx, cudaMalloc(&d1, (size_t)grid * a.n * sizeof(double)));
+    GP_CUDA(ctx, ctx->arena_alloc(reinterpret_cast<void**>(&d1), (size_t)grid * a.n * sizeof(double)));
     sate_kernel<<<grid, FTHREADS, sizeof(FactorSmem), ctx->stream>>>(a, ctx->scratch, ctx->slot_scratch_d, ctx->zbuf, ctx->slot_z_d, d1, ctx->counter);
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d1);
     if (e != cudaSuccess) return ctx->cuda_fail(e, "sate_kernel");
     if (e2 != cudaSuccess) return ctx->cuda_fail(e2, "sate_kernel");
     return GPSLC_OK;

@@ -47,9 +47,11 @@ def _data_struct(X, T, Y, nU):
 
 
 def ite(samples, X, T, Y, nU, doT, ret_idx, jitter, spp, seed=0, chain_offset=0, want_cov=False, want_samples=True, ctx=None,
-        dot_offset=0):
+        dot_offset=0, out=None):
     """samples [n_outer, n_chains, stride]; doT scalar or array. Returns dict(mean [D,C,R,n], cov [D,C,R,n,n] or None,
-    samples [D,C,R*spp,n] or None, info [D,C,R]). dot_offset: global index of doT[0] when doT is a slice of a sharded sweep."""
+    samples [D,C,R*spp,n] or None, info [D,C,R]). dot_offset: global index of doT[0] when doT is a slice of a sharded sweep.
+    out: optional dict of preallocated C-contiguous float64 arrays "mean" / "samples" of exactly those shapes (e.g. views of
+    pinned host memory that a serving loop reuses); the library writes into them instead of fresh arrays."""
     from .kernel import default_context
     ctx = ctx or default_context()
     _bind(ctx.lib); _bind_est(ctx.lib)
@@ -59,9 +61,16 @@ def ite(samples, X, T, Y, nU, doT, ret_idx, jitter, spp, seed=0, chain_offset=0,
     doT = np.ascontiguousarray(np.atleast_1d(np.asarray(doT, dtype=np.float64)))
     ret = np.ascontiguousarray(ret_idx, dtype=np.int32)
     D, R, n = doT.shape[0], ret.shape[0], d.n
-    mean = np.empty((D, C, R, n))
+    def _buf(key, shape):
+        if out is not None and key in out:
+            b = out[key]
+            if b.shape != shape or b.dtype != np.float64 or not b.flags["C_CONTIGUOUS"]:
+                raise ValueError(f"out[{key!r}] must be a C-contiguous float64 array of shape {shape}")
+            return b
+        return np.empty(shape)
+    mean = _buf("mean", (D, C, R, n))
     cov = np.empty((D, C, R, n, n)) if want_cov else None
-    smp = np.empty((D, C, R * spp, n)) if (want_samples and spp > 0) else None
+    smp = _buf("samples", (D, C, R * spp, n)) if (want_samples and spp > 0) else None
     info = np.empty((D, C, R), dtype=np.int32)
     if dot_offset:
         ctx.check(ctx.lib.gpslc_ite_slice(ctx.h, HOST, ctypes.byref(d), ptr(samples), n_outer, C, stride, ptr(ret), R, ptr(doT), D,
