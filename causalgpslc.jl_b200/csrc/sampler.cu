@@ -213,7 +213,7 @@ mh_lanes_kernel(ModelDev m, ChainDev c, const int* lane_order, int outer, int j0
     FactorSmem& sm = *reinterpret_cast<FactorSmem*>(smem_raw);
     __shared__ RbfSpec spec;
     __shared__ unsigned int job;
-    __shared__ double s_new, s_part;
+    __shared__ double s_new, s_terms[5];
     factor_smem_init(sm);
 #ifdef GPSLC_PHASE_TIMING
     const long long _k0 = clock64();
@@ -240,20 +240,30 @@ mh_lanes_kernel(ModelDev m, ChainDev c, const int* lane_order, int outer, int j0
             for (int si = m.lane_off[lane_id]; si < m.lane_off[lane_id + 1]; si++) {
                 const int s = m.lane_sites[si];
                 const SiteDef sd = m.sites[s];
+                // The scalar work of one update (proposal draw, three proposal/prior densities that depend on it, one that does not,
+                // the acceptance uniform) is spread over the first lanes of three warps in two rounds instead of running as one
+                // serial stretch on thread 0 while 255 threads wait: at n <= 256 it was ~9 % of the kernel.
+                const double cur = theta[sd.param];
+                const double shape_f = cur * cur / m.drift + 2.0, scale_f = cur * (shape_f - 1.0);
                 if (threadIdx.x == 0) {
-                    const double cur = theta[sd.param];
-                    const double shape_f = cur * cur / m.drift + 2.0, scale_f = cur * (shape_f - 1.0);
                     Stream st(m.seed, gchain, (uint32_t)s, stream_b(TAG_MH_PROP, it));
-                    const double nw = st.inv_gamma(shape_f, scale_f);
-                    const double fwd = ig_logpdf(nw, shape_f, scale_f);
-                    const double shape_b = nw * nw / m.drift + 2.0, scale_b = nw * (shape_b - 1.0);
-                    const double bwd = ig_logpdf(cur, shape_b, scale_b);
-                    const double dprior = ig_logpdf(nw, sd.pshape, sd.pscale) - ig_logpdf(cur, sd.pshape, sd.pscale);
-                    s_new = nw;
-                    s_part = dprior - fwd + bwd;
+                    s_new = st.inv_gamma(shape_f, scale_f);
+                } else if (threadIdx.x == 32) {
+                    s_terms[0] = ig_logpdf(cur, sd.pshape, sd.pscale);
+                } else if (threadIdx.x == 64) {
+                    Stream sa(m.seed, gchain, (uint32_t)s, stream_b(TAG_MH_ACC, it));
+                    s_terms[4] = log(sa.uniform());
                 }
                 __syncthreads();
                 const double nw = s_new;
+                if (threadIdx.x == 0) {
+                    s_terms[1] = ig_logpdf(nw, shape_f, scale_f);                       // forward proposal density
+                } else if (threadIdx.x == 32) {
+                    const double shape_b = nw * nw / m.drift + 2.0, scale_b = nw * (shape_b - 1.0);
+                    s_terms[2] = ig_logpdf(cur, shape_b, scale_b);                      // backward proposal density
+                } else if (threadIdx.x == 64) {
+                    s_terms[3] = ig_logpdf(nw, sd.pshape, sd.pscale);
+                }
                 double dlik;
                 if (f >= 0) {
                     build_spec(m, c, chain, f, Ubase, sd.param, nw, &spec);
@@ -262,6 +272,7 @@ mh_lanes_kernel(ModelDev m, ChainDev c, const int* lane_order, int outer, int j0
                     factor_run(gen, NCB, NCB, 1, my_scratch, my_z, sm, pipe);
                     dlik = 0.0;
                 } else {
+                    __syncthreads();
                     dlik = 0.0;
                 }
                 if (threadIdx.x == 0) {
@@ -275,10 +286,10 @@ mh_lanes_kernel(ModelDev m, ChainDev c, const int* lane_order, int outer, int j0
                         for (int k = 0; k < m.nU; k++)
                             dlik += -0.5 * (m.n * (log(nw) - log(cur)) + c.q[(size_t)chain * m.nU + k] * (1.0 / nw - 1.0 / cur));
                     }
+                    const double dprior = s_terms[3] - s_terms[0];
+                    const double s_part = dprior - s_terms[1] + s_terms[2];
                     const double alpha = s_part + dlik;
-                    Stream sa(m.seed, gchain, (uint32_t)s, stream_b(TAG_MH_ACC, it));
-                    const double u = sa.uniform();
-                    if (log(u) < alpha) {
+                    if (s_terms[4] < alpha) {
                         theta[sd.param] = nw;
                         if (f >= 0) c.lp[(size_t)chain * m.nF + f] = lp_new;
                         c.accepts[(size_t)chain * m.n_sites + s] += 1ull;
