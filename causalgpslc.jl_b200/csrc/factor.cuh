@@ -8,11 +8,15 @@
 // Algorithm: left-looking, 64-wide panels. For panel j
 //   diag tile : C_jj = K_jj - sum_{J<j} L_jJ L_jJ^T          (DMMA m8n8k4, operands streamed by TMA bulk copies)
 //               w_j  = y_j  - sum_{J<j} L_jJ z_J             (fused in the same k-loop, plain DFMA)
-//   P2        : L_jj = chol(C_jj) (warp-shuffle 16x16 panels), Linv = L_jj^-1, z_j = Linv w_j, logdet += ...
-//   row tiles : C_Ij = K_Ij - sum_J L_IJ L_jJ^T  (128x64 per tile) ; L_Ij = C_Ij Linv^T (DMMA, A-fragments rebuilt
-//               from the accumulators with quad shuffles) ; L_Ij stored to the CTA's global scratch.
+//   P2        : [L_jj ; z_j^T] = Cholesky of the bordered block [C_jj w_j ; w_j^T .] in shared memory, right-looking over
+//               8-column tiles: 8x8 pivot tiles by one warp in registers, everything else 8x8x4 DMMAs; leaves the inverses of
+//               the 8x8 diagonal tiles and -L_jj (below them) as B-fragment atoms for the row tiles
+//   row tiles : C_Ij = K_Ij - sum_J L_IJ L_jJ^T  (128x64 per tile, non-inlined spill-free k-loop) ; L_Ij = C_Ij L_jj^-T by block
+//               forward substitution over 8-column tiles (DMMA, A-fragments rebuilt from accumulator-layout values with quad
+//               shuffles) ; L_Ij stored to the CTA's global scratch.
 // L lives in global scratch in an "atom" layout: every 8(row) x 4(k) DMMA operand fragment is 256 contiguous bytes,
-// fragments are grouped into 64(row) x 8(k) slabs of 4 KB so that one cp.async.bulk moves one pipeline operand.
+// fragments are grouped into 64(row) x 16(k) slabs of 8 KB so that one cp.async.bulk moves one pipeline operand.
+// DESIGN.md §3.1 has the rationale of each piece and profiles/phase_timing_r01.md what it bought.
 #pragma once
 #include <type_traits>
 #include "common.cuh"
@@ -30,9 +34,6 @@ static __device__ unsigned long long g_phase_cycles[24];
 #define GP_PHASE_MARK(k) do {} while (0)
 #endif
 
-#ifndef GPSLC_POTF2_VARIANT
-#define GPSLC_POTF2_VARIANT 3
-#endif
 constexpr int NB = 64;                 // panel width == row-block height
 constexpr int KB = 16;                 // k extent of one pipeline slab
 constexpr int K4S = KB / 4;            // 8x4 operand atoms along k per slab
@@ -57,7 +58,8 @@ struct FactorOut {
 
 struct __align__(128) FactorSmem {
     double stage[STAGES * STAGE_D];    // 72 KB; P2 aliases it as workspace while no copy is in flight
-    double linv[LINV_D];               // 18 KB; inverse of the current diagonal block: the 72 8x4 atoms on/below the diagonal
+    double linv[LINV_D];               // 18 KB; what the row-tile epilogue needs of the current diagonal block, as the 72 8x4 B-fragment
+                                       // atoms on/below the diagonal: inverses of the 8x8 diagonal tiles, minus L_jj below them
     double colfeat[CF_DIMS * NB];      // 12 KB; feature values of the current panel's 64 columns (covariance generation)
     double exp2tab[32];                // 2^(i/32) for the generators' exponential; must directly follow colfeat
     double p2buf[72];                  // pivot-warp broadcast buffer: an 8x8 column block of L and the 8 reciprocal pivots
@@ -79,9 +81,6 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t coun
 }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
     uint32_t ok;
@@ -148,8 +147,6 @@ __host__ __device__ inline size_t scratch_doubles(int NRB, int /*NCB*/) { return
 __device__ __host__ inline int elem_off(int r, int c) {
     return (c / KB) * SLAB_D + (r >> 3) * (K4S * 32) + ((c >> 2) % K4S) * 32 + (r & 7) * 4 + (c & 3);
 }
-__device__ __forceinline__ int linv_off(int n, int k) { return ((n >> 3) * ((n >> 3) + 1) + (k >> 2)) * 32 + (n & 7) * 4 + (k & 3); }
-__device__ __forceinline__ bool linv_has(int n, int k) { return (k >> 2) <= 2 * (n >> 3) + 1; }
 
 // 2^(i/32), correctly rounded (see exp_neg_tab in gens.cuh)
 static __device__ const double GPSLC_EXP2_TAB[32] = {
@@ -343,7 +340,8 @@ __device__ inline void p2_factor_diag(FactorSmem& sm, double* Cs, int col0) {
 }
 
 // ---------------------------------------------------------------------------------------------- main routine
-struct Pipe { uint32_t produced; uint32_t consumed; };
+struct Pipe { uint32_t produced; uint32_t consumed; };   // slab sequence numbers of the operand ring (produced is kept equal to
+                                                         // consumed at phase boundaries; the ring itself tracks only consumed)
 
 // Row-tile operand producer: slab t of tile `tile` of panel j (A rows of blocks I0 [, I0+1] and the B rows of block j) goes
 // into pipeline slot gi, whose stage must be free. Called by one lane.
