@@ -1,5 +1,6 @@
 // extern "C" surface of libgpslc_b200.so (include/gpslc.h).
 #include "../../include/gpslc.h"
+#include <cstdlib>
 #include "capi_util.cuh"
 
 namespace gpslc {
@@ -351,6 +352,7 @@ static int est_common(gpslc_ctx* h, int loc, const gpslc_data* d, const double* 
     a.X = dX.d; a.T = dT.d; a.Y = dY.d; a.samples = dS.d; a.n_chains = n_chains; a.ret_idx = dRet.d; a.R = R;
     a.doT = dDo.d; a.n_doT = n_doT; a.jitter = jitter; a.spp = spp; a.seed = seed; a.chain0 = chain_offset;
     a.var_as_std = var_as_std; a.dot0 = dot_offset;
+    { const char* e = getenv("GPSLC_LS_UNSQUARED"); a.ls_unsquared = (e && atoi(e) == 1) ? 1 : 0; }
     GP_TRY(dInfo.outbuf(loc, info, tasks));
     a.info = dInfo.d;
     int rc;

@@ -18,6 +18,7 @@ struct EstArgs {
     double* msate; double* vsate;   // [n_doT][C][R]
     double* sate_out;               // [n_doT][C][R*spp]
     int var_as_std;
+    int ls_unsquared;               // experiment knob, see sampler.cuh
     int dot0;                       // global index of doT[0] (sharded sweeps): only the draws' RNG streams depend on it
 };
 

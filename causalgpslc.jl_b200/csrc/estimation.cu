@@ -155,19 +155,19 @@ __device__ inline void fill_ite_spec(const EstArgs& a, const double* rec, double
         if (d < nU) {
             sp->feat[d] = rec + a.n_params + (size_t)d * a.n;
             const double ls = rec[6 + 4 * nX + nU + d];           // uyLS
-            sp->w[d] = 1.0 / (ls * ls); sp->sw[d] = 1.0 / ls;
+            sp->w[d] = a.ls_unsquared ? 1.0 / ls : 1.0 / (ls * ls); sp->sw[d] = a.ls_unsquared ? rsqrt(ls) : 1.0 / ls;
         } else {
             const int k = d - nU;
             sp->feat[d] = a.X + (size_t)k * a.n;
             const double ls = rec[6 + 3 * nX + k];                // xyLS
-            sp->w[d] = 1.0 / (ls * ls); sp->sw[d] = 1.0 / ls;
+            sp->w[d] = a.ls_unsquared ? 1.0 / ls : 1.0 / (ls * ls); sp->sw[d] = a.ls_unsquared ? rsqrt(ls) : 1.0 / ls;
         }
     }
     if (threadIdx.x == 0) {
         sp->D = nU + nX; sp->n = a.n; sp->npad = ceil_div(a.n, NB) * NB;
         sp->T = a.T; sp->Y = a.Y;
         const double tyLS = rec[3];
-        sp->wT = 1.0 / (tyLS * tyLS); sp->swT = 1.0 / tyLS;
+        sp->wT = a.ls_unsquared ? 1.0 / tyLS : 1.0 / (tyLS * tyLS); sp->swT = a.ls_unsquared ? rsqrt(tyLS) : 1.0 / tyLS;
         sp->doT = doT; sp->yNoise = rec[2]; sp->yScale = rec[5]; sp->jitter = a.jitter;
     }
 }

@@ -83,8 +83,8 @@ __device__ inline void build_spec(const ModelDev& m, const ChainDev& c, int chai
         spec->feat[d] = (kind == SRC_U) ? Ubase + (size_t)idx * m.n : (kind == SRC_X) ? Xm + (size_t)idx * m.n : Td;
         const int p = fd.ls_param[d];
         const double ls = (p == ov_param) ? ov_val : theta[p];
-        spec->w[d] = 1.0 / (ls * ls);
-        spec->sw[d] = 1.0 / ls;
+        spec->w[d] = m.ls_unsquared ? 1.0 / ls : 1.0 / (ls * ls);
+        spec->sw[d] = m.ls_unsquared ? rsqrt(ls) : 1.0 / ls;
     }
     if (threadIdx.x == 0) {
         spec->D = fd.D;
@@ -651,6 +651,7 @@ int sampler_create(Ctx* ctx, int loc, int n, int nX, int nU, int binary, const d
     m.u_layout_reference = (u_layout_mode == 0) ? 1 : 0;
     m.ess_rule = ess_rule;
     m.eps = eps; m.cov = cov; m.dU = (1.0 + eps) - cov; m.drift = drift;
+    { const char* e = getenv("GPSLC_LS_UNSQUARED"); m.ls_unsquared = (e && atoi(e) == 1) ? 1 : 0; }
     m.seed = seed; m.chain0 = chain_offset; m.n_chains = n_chains;
     m.nMH = (!has_u && !has_x) ? 1 : nMH;   // inference.jl:157-160: three sites once per outer iteration
     m.nES = nES;

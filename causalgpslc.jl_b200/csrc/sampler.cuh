@@ -44,6 +44,7 @@ struct ModelDev {
     unsigned long long seed;
     int chain0, n_chains;
     int nMH, nES;
+    int ls_unsquared;               // experiment knob (GPSLC_LS_UNSQUARED=1): kernel exp(-d^2 / ls) instead of exp(-d^2 / ls^2), see DESIGN.md §5
 };
 
 struct ChainDev {

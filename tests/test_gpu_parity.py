@@ -396,6 +396,45 @@ def test_public_api_shapes_and_golden_gate(ctx, kats):
     assert xyLS is None and U.shape == (150, 1) and tyLS > 0
 
 
+def _golden_match(ctx, name, doT, chains=16, seed=100):
+    """Per-chain (fraction of mean ITEs inside the golden 90 % interval, correlation of the mean ITEs with the golden means)."""
+    import pandas as pd
+    gobj = g.gpslc(os.path.join(GOLD, "data", name + ".csv"), seed=seed, n_chains=chains, ctx=ctx)
+    assert g.getN(gobj) == 200 and gobj.X.shape == (200, 3) and len(gobj.posteriorSamples) == 24
+    ite = g.sampleITE(gobj, float(doT), all_chains=True, ctx=ctx)             # [C, n, R*spp]
+    assert ite.shape == (chains, 200, 150) and np.all(np.isfinite(ite))
+    exp = pd.read_csv(os.path.join(GOLD, "results", f"{name}_{doT}.csv"))
+    means = ite.mean(axis=2)
+    inside = ((exp["LowerBound"].values[None] <= means) & (means <= exp["UpperBound"].values[None])).mean(axis=1)
+    corr = np.array([np.corrcoef(m, exp["Mean"].values)[0, 1] for m in means])
+    return inside, corr
+
+
+@pytest.mark.parametrize("name,min_corr,all_pass_gate", [("multiplicative_linear", 0.9, True), ("multiplicative_nonlinear", 0.6, False),
+                                                         ("additive_nonlinear", 0.7, False)])
+def test_synthetic_golden_fixtures(ctx, name, min_corr, all_pass_gate):
+    """The reference ships four synthetic n=200 datasets (T, Y, X1..X3, obj) with golden ITE summaries at doT = 0 and 1
+    (test/test_results/<name>_{0,1}.csv) but no test that uses them. Default hyperparameters, 16 chains, whole
+    path gpslc -> sampleITE. The chains differ from the reference's (Philox vs Julia's Xoshiro) and a default run is only 24
+    outer iterations, so the check is distributional: the individuals' mean ITEs must be strongly correlated with the golden
+    means in the typical chain, and for multiplicative_linear every chain must also pass the reference's own gate (at least
+    half of the mean ITEs inside the golden 90 % interval, test/driver.jl:46-52). Measured match rates for all fixtures, and the
+    open question about additive_linear and NEEC at doT = 1, are in DESIGN.md §5 (tools/gpu_golden_probe.py)."""
+    for doT in (0, 1):
+        inside, corr = _golden_match(ctx, name, doT)
+        print(name, doT, "inside: median %.2f min %.2f; corr: median %.2f" % (np.median(inside), inside.min(), np.median(corr)))
+        assert np.median(corr) >= min_corr, (name, doT, np.median(corr))
+        if all_pass_gate:
+            assert inside.min() >= 0.5, (name, doT, inside.min())
+
+
+@pytest.mark.xfail(reason="open parity question (DESIGN.md §5): with the kernel convention of the reference's current source the mean "
+                          "ITEs of additive_linear come out anti-correlated with the untested golden file", strict=False)
+def test_synthetic_golden_additive_linear(ctx):
+    inside, corr = _golden_match(ctx, "additive_linear", 0)
+    assert np.median(corr) >= 0.5
+
+
 def test_gpslc_accepts_the_four_csv_shapes(ctx):
     """test/gpslc.jl: full / no covariates / no objects / neither, with nOuter=5, nMHInner=1, nESInner=1."""
     for f, has_u, has_x in (("minimal.csv", True, True), ("no_cov.csv", True, False), ("no_objects.csv", False, True),
