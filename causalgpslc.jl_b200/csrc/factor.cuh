@@ -97,6 +97,21 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// same copy with an L2 eviction-priority hint (createpolicy): the B slabs of a panel are re-read by every row tile of the panel,
+// the A slabs are streamed once per panel
+#ifndef GPSLC_L2_HINTS
+#define GPSLC_L2_HINTS 1
+#endif
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, unsigned long long* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // Stage release without an "empty" mbarrier and without a waiting producer: every warp counts itself out of a stage with an
 // acq_rel shared-memory atomic; the warp that arrives last (and only that one) resets the counter and immediately issues the
@@ -353,9 +368,16 @@ __device__ __forceinline__ void issue_row_slab(FactorSmem& sm, const double* scr
     mbar_expect_tx(&sm.full[st], (two ? 3 : 2) * SLAB_D * 8);
     double* dst = sm.stage + st * STAGE_D;
     const size_t so = (size_t)t * SLAB_D;
+#if GPSLC_L2_HINTS
+    const uint64_t pa = l2_policy_evict_first(), pb = l2_policy_evict_last();
+    bulk_g2s_hint(dst, scratch + row_off(I0) + so, SLAB_D * 8, &sm.full[st], pa);
+    if (two) bulk_g2s_hint(dst + SLAB_D, scratch + row_off(I0 + 1) + so, SLAB_D * 8, &sm.full[st], pa);
+    bulk_g2s_hint(dst + 2 * SLAB_D, scratch + row_off(j) + so, SLAB_D * 8, &sm.full[st], pb);
+#else
     bulk_g2s(dst, scratch + row_off(I0) + so, SLAB_D * 8, &sm.full[st]);
     if (two) bulk_g2s(dst + SLAB_D, scratch + row_off(I0 + 1) + so, SLAB_D * 8, &sm.full[st]);
     bulk_g2s(dst + 2 * SLAB_D, scratch + row_off(j) + so, SLAB_D * 8, &sm.full[st]);
+#endif
 }
 
 // The k-loop of one row tile, slabs [tb, te): acc -= nothing yet, acc += A_slab x B_slab^T over the slabs. It is a separate
@@ -490,7 +512,12 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
             auto issue_diag_slab = [&](const int t2, const uint32_t gi) {
                 const int st = gi % STAGES;
                 mbar_expect_tx(&sm.full[st], DS * SLAB_D * 8);
+#if GPSLC_L2_HINTS
+                bulk_g2s_hint(sm.stage + st * STAGE_D + SLAB_D, scratch + row_off(j) + (size_t)t2 * DS * SLAB_D, DS * SLAB_D * 8, &sm.full[st],
+                              l2_policy_evict_last());     // the row tiles of this panel read the same slabs again
+#else
                 bulk_g2s(sm.stage + st * STAGE_D + SLAB_D, scratch + row_off(j) + (size_t)t2 * DS * SLAB_D, DS * SLAB_D * 8, &sm.full[st]);
+#endif
             };
             for (int t2 = 0; t2 < STAGES && t2 < T2; t2++) {
                 const uint32_t gi = pipe.consumed + t2;
