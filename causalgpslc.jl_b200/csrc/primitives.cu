@@ -9,13 +9,15 @@ namespace gpslc {
 int ensure_workspace(Ctx* ctx, int NRB, int NCB, long long tasks, int* grid_out, int team) {
     const size_t need = scratch_doubles(NRB, NCB);
     const size_t needz = (size_t)2 * MAXRHS * NCB * NB;
-    if (ctx->slots == 0) {
-        const char* e = getenv("GPSLC_CTAS_PER_SM");   // development knob: resident factor CTAs per SM (default 2)
-        const int per = (e && atoi(e) > 0) ? atoi(e) : 2;
-        ctx->slots = per * ctx->num_sms;
-    }
+    if (ctx->slots == 0) ctx->slots = 2 * ctx->num_sms;   // upper bound on the grid of any factor kernel (sizes per-slot side buffers)
+    // Resident factor CTAs per SM for this launch: two, so that one CTA's serial phases overlap the other's tensor work - except
+    // for few large tasks (measured: 32 chains at n = 8192 run at 0.80 of peak with one CTA per SM and 0.42 with two, because the
+    // second wave is nearly empty and every task runs at half speed). GPSLC_CTAS_PER_SM overrides (development knob).
+    const char* e = getenv("GPSLC_CTAS_PER_SM");
+    int per = (e && atoi(e) > 0) ? atoi(e) : ((team == 1 && NCB >= 32 && tasks <= 3LL * ctx->num_sms) ? 1 : 2);
+    if (per > 2) per = 2;
     // team > 1: one L scratch per team (cluster), one z buffer per CTA; *grid_out is the number of teams
-    const long long max_slots = ctx->slots / team;
+    const long long max_slots = (long long)per * ctx->num_sms / team;
     long long grid = tasks < max_slots ? tasks : max_slots;
     if (grid < 1) grid = 1;
     if ((size_t)grid * need > ctx->scratch_cap_d) {
