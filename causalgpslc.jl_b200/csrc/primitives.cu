@@ -12,9 +12,10 @@ int ensure_workspace(Ctx* ctx, int NRB, int NCB, long long tasks, int* grid_out,
     if (ctx->slots == 0) ctx->slots = 2 * ctx->num_sms;   // upper bound on the grid of any factor kernel (sizes per-slot side buffers)
     // Resident factor CTAs per SM for this launch: two, so that one CTA's serial phases overlap the other's tensor work - except
     // for few large tasks (measured: 32 chains at n = 8192 run at 0.80 of peak with one CTA per SM and 0.42 with two, because the
-    // second wave is nearly empty and every task runs at half speed). GPSLC_CTAS_PER_SM overrides (development knob).
+    // second wave is nearly empty and every task runs at half speed; n = 2048, 64 chains: two CTAs 0.75, one 0.73; n = 4096, 64
+    // chains: two 0.81, one 0.83). GPSLC_CTAS_PER_SM overrides (development knob).
     const char* e = getenv("GPSLC_CTAS_PER_SM");
-    int per = (e && atoi(e) > 0) ? atoi(e) : ((team == 1 && NCB >= 32 && tasks <= 3LL * ctx->num_sms) ? 1 : 2);
+    int per = (e && atoi(e) > 0) ? atoi(e) : ((team == 1 && ((NCB >= 32 && tasks <= 3LL * ctx->num_sms) || (NCB >= 64 && tasks <= 6LL * ctx->num_sms))) ? 1 : 2);
     if (per > 2) per = 2;
     // team > 1: one L scratch per team (cluster), one z buffer per CTA; *grid_out is the number of teams
     const long long max_slots = (long long)per * ctx->num_sms / team;
