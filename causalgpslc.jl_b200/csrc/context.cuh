@@ -74,5 +74,7 @@ struct ArenaScope {
 // resident CTA, fewer when there are fewer tasks or when the slots would not fit in free HBM (large n). With team > 1 (cluster
 // launches, factor.cuh) a slot of L scratch serves a whole team and *grid is the number of teams.
 int ensure_workspace(Ctx* ctx, int NRB, int NCB, long long tasks, int* grid, int team = 1);
+// cluster size (1, 2, 4 or 8 CTAs per matrix) for a launch with `tasks` independent factorizations of NCB block columns
+int pick_team(Ctx* ctx, long long tasks, int NCB);
 
 }  // namespace gpslc

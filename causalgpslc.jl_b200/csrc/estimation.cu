@@ -333,7 +333,7 @@ sate_kernel(EstArgs a, double* scratch, size_t slot_scratch, double* zbuf, size_
         }
         for (int k = threadIdx.x; k < spec.D; k += blockDim.x) { rspec.feat[k] = spec.feat[k]; rspec.w[k] = spec.w[k]; rspec.sw[k] = sqrt(spec.w[k]); }
         __syncthreads();
-        RbfGen rgen{&rspec};
+        RbfGen rgen{&rspec, sm.exp2tab};
         factor_run(rgen, NCB, NCB, 2, my_scratch, my_z, sm, pipe);
         if (threadIdx.x == 0) {
             const FactorOut o = sm.out;
@@ -355,16 +355,6 @@ sate_kernel(EstArgs a, double* scratch, size_t slot_scratch, double* zbuf, size_
         }
         __syncthreads();
     }
-}
-
-// Team size for `tasks` independent factorizations with NCB block columns: the largest power of two (<= 8, the portable cluster
-// limit) that still leaves every task a team of its own among the resident CTAs. GPSLC_TEAM overrides (development knob).
-static int pick_team(Ctx* ctx, long long tasks, int NCB) {
-    if (const char* e = getenv("GPSLC_TEAM")) { const int g = atoi(e); if (g == 1 || g == 2 || g == 4 || g == 8) return g; }
-    const long long resident = 2LL * ctx->num_sms;
-    int g = 1;
-    while (g < 8 && tasks * (2 * g) <= resident && 4 * (2 * g) <= NCB) g *= 2;
-    return g;
 }
 
 int launch_ite(Ctx* ctx, const EstArgs& a) {

@@ -75,45 +75,27 @@ struct RbfSpec {
     int D, n;
 };
 
+// The strip() fast path and the element-wise one() (ragged edges) must give bit-identical values for the same entry: which of
+// the two evaluates an entry depends on how the row blocks are tiled (one CTA or a cluster team, 64- or 128-row tiles), and a
+// chain is required not to depend on that (nor, through the team size, on how many chains run beside it). Both therefore use
+// the same operations in the same order, written with explicit round-to-nearest intrinsics so that the compiler cannot contract
+// a multiply-add in one path and not in the other.
 struct RbfGen {
     const RbfSpec* s;
+    const double* tab;          // FactorSmem::exp2tab
     __device__ __forceinline__ double one(int r, int c) const {
         if (r >= s->n || c >= s->n) return (r == c) ? 1.0 : 0.0;
         double a = 0.0;
         for (int d = 0; d < s->D; d++) {
             const double* p = s->feat[d];
-            const double t = p[r] - p[c];
-            a = fma(t * s->w[d], t, a);
+            const double w = s->sw[d];
+            const double t = __dsub_rn(__dmul_rn(__ldg(p + r), w), __dmul_rn(__ldg(p + c), w));
+            a = __fma_rn(t, t, a);
         }
-        double v = s->scale * exp(-a);
-        if (r == c) v += s->noise;
-        return v;
+        return __fma_rn(s->scale, exp_neg_tab(a, tab), (r == c) ? s->noise : 0.0);
     }
     __device__ __forceinline__ void quad(int r0, int r1, int c, double& v00, double& v01, double& v10, double& v11) const {
-        const int n = s->n;
-        if (r1 < n && r0 < n && c + 1 < n) {
-            double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
-            const int D = s->D;
-            for (int d = 0; d < D; d++) {
-                const double* p = s->feat[d];
-                const double w = s->w[d];
-                const double z0 = p[r0], z1 = p[r1], c0 = p[c], c1 = p[c + 1];
-                double t;
-                t = z0 - c0; a00 = fma(t * w, t, a00);
-                t = z0 - c1; a01 = fma(t * w, t, a01);
-                t = z1 - c0; a10 = fma(t * w, t, a10);
-                t = z1 - c1; a11 = fma(t * w, t, a11);
-            }
-            const double sc = s->scale;
-            v00 = sc * exp(-a00); v01 = sc * exp(-a01); v10 = sc * exp(-a10); v11 = sc * exp(-a11);
-            const double nz = s->noise;
-            if (r0 == c) v00 += nz;
-            if (r0 == c + 1) v01 += nz;
-            if (r1 == c) v10 += nz;
-            if (r1 == c + 1) v11 += nz;
-        } else {
-            v00 = one(r0, c); v01 = one(r0, c + 1); v10 = one(r1, c); v11 = one(r1, c + 1);
-        }
+        v00 = one(r0, c); v01 = one(r0, c + 1); v10 = one(r1, c); v11 = one(r1, c + 1);
     }
     // NI column pairs (c0 + 8*ni, +1) for rows r0 and (unless ONE_ROW) r1: the accumulator layout of one warp tile.
     // Row features are loaded once per dimension for all NI pairs; all loads go through the read-only path.
@@ -123,7 +105,7 @@ struct RbfGen {
         if (!GPSLC_STAGE_COLS || D > CF_DIMS) return;
         for (int i = threadIdx.x; i < D * NB; i += blockDim.x) {
             const int d = i >> 6, c = col0 + (i & 63);
-            cf[i] = (c < s->n) ? __ldg(s->feat[d] + c) * s->sw[d] : 0.0;    // pre-scaled by 1 / lengthscale
+            cf[i] = (c < s->n) ? __dmul_rn(__ldg(s->feat[d] + c), s->sw[d]) : 0.0;    // pre-scaled by 1 / lengthscale
         }
     }
     template <int NI, bool ONE_ROW>
@@ -141,17 +123,17 @@ struct RbfGen {
 #pragma unroll 4
                 for (int d = 0; d < D; d++) {
                     const double w = s->sw[d];
-                    const double z0 = __ldg(s->feat[d] + r0) * w;
-                    const double z1 = ONE_ROW ? z0 : __ldg(s->feat[d] + r1) * w;
+                    const double z0 = __dmul_rn(__ldg(s->feat[d] + r0), w);
+                    const double z1 = ONE_ROW ? z0 : __dmul_rn(__ldg(s->feat[d] + r1), w);
 #pragma unroll
                     for (int ni = 0; ni < NI; ni++) {
                         const double2 cc = *reinterpret_cast<const double2*>(cf + d * NB + cl + 8 * ni);
                         double t;
-                        t = z0 - cc.x; a[0][ni][0] = fma(t, t, a[0][ni][0]);
-                        t = z0 - cc.y; a[0][ni][1] = fma(t, t, a[0][ni][1]);
+                        t = __dsub_rn(z0, cc.x); a[0][ni][0] = __fma_rn(t, t, a[0][ni][0]);
+                        t = __dsub_rn(z0, cc.y); a[0][ni][1] = __fma_rn(t, t, a[0][ni][1]);
                         if (!ONE_ROW) {
-                            t = z1 - cc.x; a[1][ni][0] = fma(t, t, a[1][ni][0]);
-                            t = z1 - cc.y; a[1][ni][1] = fma(t, t, a[1][ni][1]);
+                            t = __dsub_rn(z1, cc.x); a[1][ni][0] = __fma_rn(t, t, a[1][ni][0]);
+                            t = __dsub_rn(z1, cc.y); a[1][ni][1] = __fma_rn(t, t, a[1][ni][1]);
                         }
                     }
                 }
@@ -159,31 +141,30 @@ struct RbfGen {
                 for (int d = 0; d < D; d++) {
                     const double* p = s->feat[d];
                     const double w = s->sw[d];
-                    const double z0 = __ldg(p + r0) * w;
-                    const double z1 = ONE_ROW ? z0 : __ldg(p + r1) * w;
+                    const double z0 = __dmul_rn(__ldg(p + r0), w);
+                    const double z1 = ONE_ROW ? z0 : __dmul_rn(__ldg(p + r1), w);
 #pragma unroll
                     for (int ni = 0; ni < NI; ni++) {
-                        const double c0v = __ldg(p + c0 + 8 * ni) * w, c1v = __ldg(p + c0 + 8 * ni + 1) * w;
+                        const double c0v = __dmul_rn(__ldg(p + c0 + 8 * ni), w), c1v = __dmul_rn(__ldg(p + c0 + 8 * ni + 1), w);
                         double t;
-                        t = z0 - c0v; a[0][ni][0] = fma(t, t, a[0][ni][0]);
-                        t = z0 - c1v; a[0][ni][1] = fma(t, t, a[0][ni][1]);
+                        t = __dsub_rn(z0, c0v); a[0][ni][0] = __fma_rn(t, t, a[0][ni][0]);
+                        t = __dsub_rn(z0, c1v); a[0][ni][1] = __fma_rn(t, t, a[0][ni][1]);
                         if (!ONE_ROW) {
-                            t = z1 - c0v; a[1][ni][0] = fma(t, t, a[1][ni][0]);
-                            t = z1 - c1v; a[1][ni][1] = fma(t, t, a[1][ni][1]);
+                            t = __dsub_rn(z1, c0v); a[1][ni][0] = __fma_rn(t, t, a[1][ni][0]);
+                            t = __dsub_rn(z1, c1v); a[1][ni][1] = __fma_rn(t, t, a[1][ni][1]);
                         }
                     }
                 }
             }
             const double sc = s->scale, nz = s->noise;
-            const double* tab = cf + CF_DIMS * NB;   // FactorSmem::exp2tab follows colfeat
 #pragma unroll
             for (int ni = 0; ni < NI; ni++) {
                 const int c = c0 + 8 * ni;
-                v[0][ni][0] = fma(sc, exp_neg_tab(a[0][ni][0], tab), (r0 == c) ? nz : 0.0);
-                v[0][ni][1] = fma(sc, exp_neg_tab(a[0][ni][1], tab), (r0 == c + 1) ? nz : 0.0);
+                v[0][ni][0] = __fma_rn(sc, exp_neg_tab(a[0][ni][0], tab), (r0 == c) ? nz : 0.0);
+                v[0][ni][1] = __fma_rn(sc, exp_neg_tab(a[0][ni][1], tab), (r0 == c + 1) ? nz : 0.0);
                 if (!ONE_ROW) {
-                    v[1][ni][0] = fma(sc, exp_neg_tab(a[1][ni][0], tab), (r1 == c) ? nz : 0.0);
-                    v[1][ni][1] = fma(sc, exp_neg_tab(a[1][ni][1], tab), (r1 == c + 1) ? nz : 0.0);
+                    v[1][ni][0] = __fma_rn(sc, exp_neg_tab(a[1][ni][0], tab), (r1 == c) ? nz : 0.0);
+                    v[1][ni][1] = __fma_rn(sc, exp_neg_tab(a[1][ni][1], tab), (r1 == c + 1) ? nz : 0.0);
                 }
             }
         } else {

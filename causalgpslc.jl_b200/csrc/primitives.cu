@@ -49,6 +49,17 @@ int ensure_workspace(Ctx* ctx, int NRB, int NCB, long long tasks, int* grid_out,
     return GPSLC_OK;
 }
 
+// Team size for `tasks` independent factorizations with NCB block columns: the largest power of two (<= 8, the portable cluster
+// limit) that still leaves every task a team of its own among the resident CTAs and keeps the redundant diagonal work of a
+// team (about 1.7 * team / NCB of the total) moderate. GPSLC_TEAM overrides (development knob).
+int pick_team(Ctx* ctx, long long tasks, int NCB) {
+    if (const char* e = getenv("GPSLC_TEAM")) { const int g = atoi(e); if (g == 1 || g == 2 || g == 4 || g == 8) return g; }
+    const long long resident = 2LL * ctx->num_sms;
+    int g = 1;
+    while (g < 8 && tasks * (2 * g) <= resident && 4 * (2 * g) <= NCB) g *= 2;
+    return g;
+}
+
 // ------------------------------------------------------------------------------------------------ cov build
 // Materialised covariance (HBM-bound): K[b] (n x n, column-major) for `batch` parameter sets. One thread computes a
 // 1x4 strip of a column block so that stores are 32-byte vectors along the fastest (row) dimension.
@@ -172,7 +183,7 @@ batched_logpdf_kernel(int batch, int n, const double* __restrict__ Kall, int ld,
                 spec.sw[d] = sqrt(spec.w[d]);
             }
             __syncthreads();
-            RbfGen gen{&spec};
+            RbfGen gen{&spec, sm.exp2tab};
             factor_run(gen, NCB, NCB, 1, my_scratch, my_z, sm, pipe);
         } else {
             DenseGen gen{Kall + (size_t)b * ld * n, {y, y}, n, ld};

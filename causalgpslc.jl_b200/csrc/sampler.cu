@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(256) refresh_chains_kernel(ModelDev m, ChainDe
 
 // ------------------------------------------------------------------------------------------------ factor evaluation
 // tasks = (chain from list or all chains) x (existing factors); writes lp / lpP
+template <int TEAM>
 __global__ void __launch_bounds__(FTHREADS, 2)
 eval_factors_kernel(ModelDev m, ChainDev c, const int* list, const unsigned int* n_list_dev, int n_all, const int* exist,
                     int n_exist, int proposed, double* scratch, size_t slot_scratch, double* zbuf, size_t slot_z,
@@ -175,23 +176,31 @@ eval_factors_kernel(ModelDev m, ChainDev c, const int* list, const unsigned int*
     factor_smem_init(sm);
     Pipe pipe{0, 0};
     const int NCB = ceil_div(m.n, NB);
-    double* my_scratch = scratch + (size_t)blockIdx.x * slot_scratch;
+    // TEAM = 1: one thread-block cluster per task (few large tasks), see factor.cuh; tasks dealt round-robin to the clusters
+    const int trank = TEAM ? (int)cluster_rank() : 0;
+    const unsigned int team = TEAM ? cluster_id_x() : blockIdx.x, nteams = TEAM ? cluster_count_x() : gridDim.x;
+    double* my_scratch = scratch + (size_t)team * slot_scratch;
     double* my_z = zbuf + (size_t)blockIdx.x * slot_z;
     const unsigned int n_list = list ? *n_list_dev : (unsigned)n_all;
     const unsigned int total = n_list * (unsigned)n_exist;
-    for (;;) {
-        if (threadIdx.x == 0) job = atomicAdd(counter, 1u);
-        __syncthreads();
-        const unsigned int t = job;
+    for (unsigned int round = 0;; round++) {
+        unsigned int t;
+        if constexpr (TEAM != 0) {
+            t = team + round * nteams;
+        } else {
+            if (threadIdx.x == 0) job = atomicAdd(counter, 1u);
+            __syncthreads();
+            t = job;
+        }
         if (t >= total) break;
         const int li = t / n_exist, f = exist[t - li * n_exist];
         const int chain = list ? list[li] : li;
         const double* Ubase = (proposed ? c.UeffP : c.Ueff) + (size_t)chain * m.nU * m.n;
         build_spec(m, c, chain, f, Ubase, -1, 0.0, &spec);
         __syncthreads();
-        RbfGen gen{&spec};
-        factor_run(gen, NCB, NCB, 1, my_scratch, my_z, sm, pipe);
-        if (threadIdx.x == 0) {
+        RbfGen gen{&spec, sm.exp2tab};
+        factor_run<RbfGen, TEAM>(gen, NCB, NCB, 1, my_scratch, my_z, sm, pipe);
+        if (threadIdx.x == 0 && trank == 0) {
             const FactorOut o = sm.out;
             (proposed ? c.lpP : c.lp)[(size_t)chain * m.nF + f] = logpdf_from(o, m.n);
             if (o.info != 0) {
@@ -206,6 +215,7 @@ eval_factors_kernel(ModelDev m, ChainDev c, const int* list, const unsigned int*
 // ------------------------------------------------------------------------------------------------ MH lanes
 // One task = (chain, lane): all single-site MH updates (src/proposal.jl:32-41 + Gen `mh`) of the
 // sites feeding one GP factor, for sweeps [j0, j1) of outer iteration `outer`.
+template <int TEAM>
 __global__ void __launch_bounds__(FTHREADS, 2)
 mh_lanes_kernel(ModelDev m, ChainDev c, const int* lane_order, int outer, int j0, int j1, double* scratch, size_t slot_scratch,
                 double* zbuf, size_t slot_z, unsigned int* counter) {
@@ -220,13 +230,24 @@ mh_lanes_kernel(ModelDev m, ChainDev c, const int* lane_order, int outer, int j0
 #endif
     Pipe pipe{0, 0};
     const int NCB = ceil_div(m.n, NB);
-    double* my_scratch = scratch + (size_t)blockIdx.x * slot_scratch;
+    // TEAM = 1 (few chains at large n, e.g. the reference's single-chain gpslc() call): one thread-block cluster per (chain, lane)
+    // task. Every CTA of the team runs the whole site loop redundantly (same Philox streams, same factor results, hence the
+    // same accept decisions); the factorisations are shared (factor.cuh), the chain state is written by rank 0 only and
+    // published to the team by the cluster barrier that ends each update.
+    const int trank = TEAM ? (int)cluster_rank() : 0;
+    const unsigned int team = TEAM ? cluster_id_x() : blockIdx.x, nteams = TEAM ? cluster_count_x() : gridDim.x;
+    double* my_scratch = scratch + (size_t)team * slot_scratch;
     double* my_z = zbuf + (size_t)blockIdx.x * slot_z;
     const unsigned int total = (unsigned)m.n_chains * (unsigned)m.n_lanes;
-    for (;;) {
-        if (threadIdx.x == 0) job = atomicAdd(counter, 1u);
-        __syncthreads();
-        const unsigned int t = job;
+    for (unsigned int round = 0;; round++) {
+        unsigned int t;
+        if constexpr (TEAM != 0) {
+            t = team + round * nteams;
+        } else {
+            if (threadIdx.x == 0) job = atomicAdd(counter, 1u);
+            __syncthreads();
+            t = job;
+        }
         if (t >= total) break;
         // lanes in decreasing-work order, chains innermost: long lanes of every chain are scheduled first (LPT)
         const int lane_id = lane_order[t / m.n_chains];
@@ -268,8 +289,8 @@ mh_lanes_kernel(ModelDev m, ChainDev c, const int* lane_order, int outer, int j0
                 if (f >= 0) {
                     build_spec(m, c, chain, f, Ubase, sd.param, nw, &spec);
                     __syncthreads();
-                    RbfGen gen{&spec};
-                    factor_run(gen, NCB, NCB, 1, my_scratch, my_z, sm, pipe);
+                    RbfGen gen{&spec, sm.exp2tab};
+                    factor_run<RbfGen, TEAM>(gen, NCB, NCB, 1, my_scratch, my_z, sm, pipe);
                     dlik = 0.0;
                 } else {
                     __syncthreads();
@@ -289,13 +310,14 @@ mh_lanes_kernel(ModelDev m, ChainDev c, const int* lane_order, int outer, int j0
                     const double dprior = s_terms[3] - s_terms[0];
                     const double s_part = dprior - s_terms[1] + s_terms[2];
                     const double alpha = s_part + dlik;
-                    if (s_terms[4] < alpha) {
+                    if (s_terms[4] < alpha && trank == 0) {
                         theta[sd.param] = nw;
                         if (f >= 0) c.lp[(size_t)chain * m.nF + f] = lp_new;
                         c.accepts[(size_t)chain * m.n_sites + s] += 1ull;
                     }
                 }
-                __syncthreads();
+                if constexpr (TEAM != 0) cluster_barrier();   // rank 0's update of theta / lp is visible to the team
+                else __syncthreads();
             }
         }
     }
@@ -457,7 +479,7 @@ logit_prior_kernel(ModelDev m, ChainDev c, int mode, int outer, double* scratch,
             }
             __syncthreads();
         }
-        RbfGen gen{&spec};
+        RbfGen gen{&spec, sm.exp2tab};
         factor_run(gen, NCB, NCB, 0, my_scratch, my_z, sm, pipe);
         if (threadIdx.x == 0 && sm.out.info != 0) atomicMax(&c.info[chain], sm.out.info);
         const int ndraw = (mode == 0) ? 1 : m.nES;
@@ -514,7 +536,7 @@ ess_logit_kernel(ModelDev m, ChainDev c, int jj, uint32_t it, double* scratch, s
         __syncthreads();
         if (threadIdx.x == 0) spec.y[1] = nu;
         __syncthreads();
-        RbfGen gen{&spec};
+        RbfGen gen{&spec, sm.exp2tab};
         factor_run(gen, NCB, NCB, 2, my_scratch, my_z, sm, pipe);
         const FactorOut o = sm.out;
         const double* Td = m.T + (size_t)chain * m.tstride;
@@ -805,20 +827,48 @@ int sampler_create(Ctx* ctx, int loc, int n, int nX, int nU, int binary, const d
     return GPSLC_OK;
 }
 
+// Launch one of the two instantiations of a factor kernel: one CTA per task, or (few large tasks) one thread-block cluster of
+// `team` CTAs per task. *grid is the number of workspace slots (= teams); it is clipped to what can be resident.
+template <class K1, class KT, class... Args>
+static int launch_single_or_team(Ctx* ctx, K1 k_single, KT k_team, int team, int grid, const char* what, Args... args) {
+    if (team == 1) {
+        GP_CUDA(ctx, cudaFuncSetAttribute(k_single, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
+        k_single<<<grid, FTHREADS, sizeof(FactorSmem), ctx->stream>>>(args...);
+        ctx->launches++;
+        GP_CUDA(ctx, cudaGetLastError());
+        return GPSLC_OK;
+    }
+    GP_CUDA(ctx, cudaFuncSetAttribute(k_team, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = team; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(FTHREADS); cfg.dynamicSmemBytes = sizeof(FactorSmem); cfg.stream = ctx->stream;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.gridDim = dim3(grid * team);
+    int max_clusters = 0;
+    GP_CUDA(ctx, cudaOccupancyMaxActiveClusters(&max_clusters, k_team, &cfg));
+    if (max_clusters < 1) return ctx->fail(GPSLC_ERR_CUDA, std::string(what) + ": no resident cluster of the requested size");
+    if (grid > max_clusters) grid = max_clusters;   // fewer teams than slots: the teams loop over the tasks
+    cfg.gridDim = dim3(grid * team);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_team, args...);
+    ctx->launches++;
+    if (e != cudaSuccess) return ctx->cuda_fail(e, what);
+    return GPSLC_OK;
+}
+
 static int launch_eval(Sampler* s, const int* list, const unsigned int* n_list_dev, int n_list_host, int proposed) {
     Ctx* ctx = s->ctx;
     if (s->n_exist == 0 || n_list_host == 0) return GPSLC_OK;
-    GP_CUDA(ctx, cudaFuncSetAttribute(eval_factors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
     GP_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, sizeof(unsigned int), ctx->stream));
     const long long tasks = (long long)n_list_host * s->n_exist;
+    const int NCB = ceil_div(s->m.n, NB);
+    const int team = pick_team(ctx, tasks, NCB);
     int grid = 0;
-    GP_TRY(ensure_workspace(ctx, ceil_div(s->m.n, NB), ceil_div(s->m.n, NB), tasks, &grid));
-    eval_factors_kernel<<<grid, FTHREADS, sizeof(FactorSmem), ctx->stream>>>(s->m, s->c, list, n_list_dev, s->m.n_chains, s->d_exist,
-                                                                           s->n_exist, proposed, ctx->scratch, ctx->slot_scratch_d,
-                                                                           ctx->zbuf, ctx->slot_z_d, ctx->counter);
-    ctx->launches++;
-    GP_CUDA(ctx, cudaGetLastError());
-    return GPSLC_OK;
+    GP_TRY(ensure_workspace(ctx, NCB, NCB, tasks, &grid, team));
+    return launch_single_or_team(ctx, eval_factors_kernel<0>, eval_factors_kernel<1>, team, grid, "eval_factors_kernel", s->m, s->c, list,
+                                 n_list_dev, s->m.n_chains, (const int*)s->d_exist, s->n_exist, proposed, ctx->scratch, ctx->slot_scratch_d,
+                                 ctx->zbuf, ctx->slot_z_d, ctx->counter);
 }
 
 static int launch_logit_prior(Sampler* s, int mode, int outer) {
@@ -889,16 +939,15 @@ int sampler_set_state(Sampler* s, int loc, const double* packed) {
 int sampler_mh(Sampler* s, int outer, int j0, int j1) {
     Ctx* ctx = s->ctx;
     if (j1 <= j0) return GPSLC_OK;
-    GP_CUDA(ctx, cudaFuncSetAttribute(mh_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
     GP_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, sizeof(unsigned int), ctx->stream));
     const long long tasks = (long long)s->m.n_chains * s->m.n_lanes;
+    const int NCB = ceil_div(s->m.n, NB);
+    const int team = pick_team(ctx, tasks, NCB);
     int grid = 0;
-    GP_TRY(ensure_workspace(ctx, ceil_div(s->m.n, NB), ceil_div(s->m.n, NB), tasks, &grid));
-    mh_lanes_kernel<<<grid, FTHREADS, sizeof(FactorSmem), ctx->stream>>>(s->m, s->c, s->d_lane_order, outer, j0, j1, ctx->scratch,
-                                                                       ctx->slot_scratch_d, ctx->zbuf, ctx->slot_z_d, ctx->counter);
-    ctx->launches++;
-    GP_CUDA(ctx, cudaGetLastError());
-    return GPSLC_OK;
+    GP_TRY(ensure_workspace(ctx, NCB, NCB, tasks, &grid, team));
+    return launch_single_or_team(ctx, mh_lanes_kernel<0>, mh_lanes_kernel<1>, team, grid, "mh_lanes_kernel", s->m, s->c,
+                                 (const int*)s->d_lane_order, outer, j0, j1, ctx->scratch, ctx->slot_scratch_d, ctx->zbuf, ctx->slot_z_d,
+                                 ctx->counter);
 }
 
 // one elliptical-slice update of U_k for every chain (src/inference.jl:50-54): host loop over shrink rounds

@@ -193,6 +193,28 @@ def test_sampler_reproduces_oracle_chain(ctx, n, n_obj, nX, nU, with_u, binary):
         assert np.allclose(np.nan_to_num(want), np.nan_to_num(got[:, c, :]), rtol=1e-8, atol=1e-11)
 
 
+@pytest.mark.parametrize("binary", [False, True])
+def test_sampler_cluster_teams_match_single_cta(ctx, monkeypatch, binary):
+    """Few chains at large n run one thread-block cluster per (chain, lane) task (mh_lanes_kernel<1>, eval_factors_kernel<1>): every
+    CTA of a team replays the same site loop, the factorisations are shared. The chains must be bit-identical to the
+    one-CTA-per-task kernels for every team size (accept decisions included), here forced on small ragged problems."""
+    counts, X, T, Y = od.synthetic(150, 6, 3, seed=4)
+    if binary:
+        T = T > np.median(T)
+    md = od.model_data_from_arrays(counts, X, T, Y, nU=1)
+    outs = {}
+    for team in (1, 2, 4, 8):
+        monkeypatch.setenv("GPSLC_TEAM", str(team))
+        outs[team] = _run_pair(md, X, T, Y, counts, 3, 2, 2, 21, 3)
+    monkeypatch.delenv("GPSLC_TEAM")
+    for team in (2, 4, 8):
+        for a, b in zip(outs[1], outs[team]):
+            assert np.array_equal(a, b, equal_nan=True), team
+    want, _ = oi.posterior(md, 3, 2, 2, seed=21, chain=1)
+    got = outs[4][3][:, 1, :]
+    assert np.nanmax(np.abs(want - got) / (1e-9 + np.abs(want))) < 1e-8
+
+
 def test_sampler_option_switches(ctx):
     counts, X, T, Y = od.synthetic(60, 3, 2, seed=2)
     # column-wise U layout instead of the reference interleave; textbook ESS rule
