@@ -195,6 +195,32 @@ function predictCounterfactualEffects(g, nSamplesPerMixture::Int; fidelity::Int=
 end
 
 """
+    predictCounterfactualEffectsShard(g, nSamplesPerMixture, world_size, rank; fidelity=100, minDoT, maxDoT)
+One rank's block of the doT range of predictCounterfactualEffects (src/prediction.jl:23-36) through gpslc_ite_slice: the doT values
+are the independent units of the sweep; the draws are keyed by the global doT index, so the blocks of all ranks concatenate to
+exactly the unsharded result. Returns (ite[d_local, n, R*spp], the full doT range, offset of this block).
+"""
+function predictCounterfactualEffectsShard(g, nSamplesPerMixture::Int, world_size::Int, rank::Int; fidelity::Int=100,
+                                           minDoT=min(g.T...), maxDoT=max(g.T...), seed=UInt64(0))
+    doTrange = minDoT:(abs(maxDoT - minDoT) / fidelity):maxDoT
+    all = collect(Float64, doTrange); D = length(all)
+    base, rem = divrem(D, world_size)
+    cnt = base + (rank < rem ? 1 : 0); off = rank * base + min(rank, rem)
+    dts = all[off+1:off+cnt]
+    packed = pack(g); ret = retained(g.hyperparams); R = length(ret); n = length(g.Y)
+    Tf = Float64.(g.T); Xf = g.X === nothing ? Float64[] : Matrix{Float64}(g.X); Yf = Float64.(g.Y)
+    out = Array{Float64}(undef, n, R * nSamplesPerMixture, cnt)
+    GC.@preserve packed ret Tf Xf Yf out dts begin
+        check(ccall((:gpslc_ite_slice, LIB[]), Cint,
+                    (Ptr{Cvoid}, Cint, Ref{GpslcData}, Ptr{Cdouble}, Cint, Cint, Cint, Ptr{Cint}, Cint, Ptr{Cdouble}, Cint, Cint, Cdouble,
+                     Cint, UInt64, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cint}),
+                    CTX[], 0, data_struct(g, Tf, Xf, Yf), packed, size(packed, 3), 1, size(packed, 1), ret, R, dts, cnt, off,
+                    g.hyperparams.predictionCovarianceNoise, nSamplesPerMixture, seed, 0, C_NULL, C_NULL, out, C_NULL))
+    end
+    permutedims(out, (3, 1, 2)), doTrange, off
+end
+
+"""
     summarizeEstimates(samples; credible_interval=0.90) — the statistics of src/driver.jl:129-149 (row mean and the two
 quantiles, Julia `quantile` default) through gpslc_summarize. `samples` is the n × m matrix sampleITE returns, whose memory
 is exactly the C layout [m][n]. Returns (Mean, LowerBound, UpperBound) vectors; the DataFrame/CSV part stays in driver.jl.
