@@ -55,6 +55,7 @@ void gpslc_destroy(gpslc_ctx* h) {
     if (h->c.zbuf) cudaFree(h->c.zbuf);
     if (h->c.counter) cudaFree(h->c.counter);
     if (h->c.arena) cudaFree(h->c.arena);
+    h->c.block_cache_release();
     cudaStreamDestroy(h->c.stream);
     delete h;
 }

@@ -41,6 +41,42 @@ struct Ctx {
         for (void* p : arena_overflow) cudaFree(p);
         arena_overflow.clear();
     }
+    // Size-keyed cache of long-lived device blocks (chain state, sample buffers of a sampler): a host that creates and destroys
+    // samplers of the same shape in a loop (bench.py's e2e leg, SBC studies) re-uses the blocks instead of paying a cudaMalloc
+    // and a synchronising cudaFree for each of the ~25 buffers of every sampler. Bounded by BLOCK_CACHE_MAX bytes.
+    static constexpr size_t BLOCK_CACHE_MAX = (size_t)4 << 30;
+    std::vector<std::pair<size_t, void*>> block_cache;
+    size_t block_cache_bytes = 0;
+    static size_t block_round(size_t bytes) { return (bytes + 511) & ~(size_t)511; }
+    cudaError_t block_alloc(void** p, size_t bytes) {
+        bytes = block_round(bytes);
+        for (size_t i = 0; i < block_cache.size(); i++)
+            if (block_cache[i].first == bytes) {
+                *p = block_cache[i].second;
+                block_cache_bytes -= bytes;
+                block_cache[i] = block_cache.back();
+                block_cache.pop_back();
+                return cudaSuccess;
+            }
+        cudaError_t e = cudaMalloc(p, bytes);
+        if (e != cudaSuccess && !block_cache.empty()) {      // out of memory with blocks parked in the cache: release them and retry
+            cudaGetLastError();
+            block_cache_release();
+            e = cudaMalloc(p, bytes);
+        }
+        return e;
+    }
+    void block_free(void* p, size_t bytes) {
+        if (!p) return;
+        bytes = block_round(bytes);
+        if (block_cache_bytes + bytes <= BLOCK_CACHE_MAX) { block_cache.push_back({bytes, p}); block_cache_bytes += bytes; }
+        else cudaFree(p);
+    }
+    void block_cache_release() {
+        for (auto& b : block_cache) cudaFree(b.second);
+        block_cache.clear();
+        block_cache_bytes = 0;
+    }
     cudaError_t arena_alloc(void** p, size_t bytes) {
         bytes = (bytes + 255) & ~(size_t)255;
         arena_peak += bytes;

@@ -610,8 +610,8 @@ template <class T>
 static int dev_alloc(Sampler* s, T** p, size_t count) {
     *p = nullptr;
     if (count == 0) count = 1;
-    GP_CUDA(s->ctx, cudaMalloc((void**)p, count * sizeof(T)));
-    s->owned.push_back((void*)*p);
+    GP_CUDA(s->ctx, s->ctx->block_alloc((void**)p, count * sizeof(T)));
+    s->owned.push_back({(void*)*p, count * sizeof(T)});
     return GPSLC_OK;
 }
 template <class T>
@@ -641,8 +641,8 @@ static int param_idx(int nX, int nU, const char* name, int i, int j) {
 void sampler_free(Sampler* s) {
     if (!s) return;
     cudaStreamSynchronize(s->ctx->stream);
-    for (void* p : s->owned) cudaFree(p);
-    if (s->samples) cudaFree(s->samples);
+    for (auto& b : s->owned) s->ctx->block_free(b.first, b.second);
+    if (s->samples) s->ctx->block_free(s->samples, s->samples_bytes);
     delete s;
 }
 
@@ -877,7 +877,11 @@ static int launch_logit_prior(Sampler* s, int mode, int outer) {
     GP_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, sizeof(unsigned int), ctx->stream));
     int grid = 0;
     GP_TRY(ensure_workspace(ctx, ceil_div(s->m.n, NB), ceil_div(s->m.n, NB), s->m.n_chains, &grid));
-    if (!s->xibuf) { GP_CUDA(ctx, cudaMalloc(&s->xibuf, (size_t)ctx->slots * 4 * s->m.n * sizeof(double))); s->owned.push_back(s->xibuf); }
+    if (!s->xibuf) {
+        const size_t xb = (size_t)ctx->slots * 4 * s->m.n * sizeof(double);
+        GP_CUDA(ctx, ctx->block_alloc((void**)&s->xibuf, xb));
+        s->owned.push_back({(void*)s->xibuf, xb});
+    }
     logit_prior_kernel<<<grid, FTHREADS, sizeof(FactorSmem), ctx->stream>>>(s->m, s->c, mode, outer, ctx->scratch, ctx->slot_scratch_d,
                                                                           ctx->zbuf, ctx->slot_z_d, s->xibuf, ctx->counter);
     ctx->launches++;
@@ -979,13 +983,15 @@ int sampler_reserve_samples(Sampler* s, int n_outer_total) {
     if (n_outer_total <= s->samples_cap) return GPSLC_OK;
     double* nw = nullptr;
     const size_t per = (size_t)s->m.n_chains * s->m.stride;
-    GP_CUDA(ctx, cudaMalloc(&nw, per * n_outer_total * sizeof(double)));
+    const size_t nbytes = per * n_outer_total * sizeof(double);
+    GP_CUDA(ctx, ctx->block_alloc((void**)&nw, nbytes));
     if (s->samples) {
         GP_CUDA(ctx, cudaMemcpyAsync(nw, s->samples, per * s->outer_done * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
         GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        cudaFree(s->samples);
+        ctx->block_free(s->samples, s->samples_bytes);
     }
     s->samples = nw;
+    s->samples_bytes = nbytes;
     s->samples_cap = n_outer_total;
     return GPSLC_OK;
 }

@@ -60,11 +60,12 @@ struct Sampler {
     Ctx* ctx = nullptr;
     ModelDev m{};
     ChainDev c{};
-    std::vector<void*> owned;       // device allocations to free
+    std::vector<std::pair<void*, size_t>> owned;   // device allocations (pointer, bytes): returned to the context's block cache
     int outer_done = 0;             // outer iterations completed so far
     int sweeps_done = 0;            // MH sweeps completed inside the current outer iteration (bench stepping)
     double* samples = nullptr;      // device [nOuter_cap][C][stride]
     int samples_cap = 0;
+    size_t samples_bytes = 0;
     std::vector<int> lane_task_order;  // lanes sorted by decreasing work
     int* d_lane_order = nullptr;
     int n_exist = 0;                // number of existing GP factors
