@@ -331,6 +331,28 @@ def test_ite_sate_vs_reference_algebra(ctx, n, n_obj, nX, nU, with_u):
             assert np.allclose(ss, so["samples"][d, c], rtol=1e-7, atol=1e-12)
 
 
+def test_ite_full_size_vs_reference_algebra_n1024(ctx):
+    """BASELINE c3 size: MeanITE / CovITE / SATE of the fused 2048 x 2048 Cholesky against the oracle's line-by-line restatement
+    of likelihood.jl / estimation.jl (two LU solves, Bunch-Kaufman) on one posterior-like sample."""
+    n, n_obj, nX = 1024, 16, 10
+    counts, X, T, Y = od.synthetic(n, n_obj, nX, seed=1234)
+    spec = om.ModelSpec(n, 1, nX, False)
+    rng = np.random.default_rng(9)
+    rec = np.ones(spec.n_params + n)
+    rec[:spec.n_params] = 0.8 + 0.6 * rng.random(spec.n_params)
+    rec[2] = 0.2
+    rec[spec.n_params:] = np.repeat(rng.standard_normal(n_obj), n // n_obj)
+    ret = np.array([0], dtype=np.int32)
+    out = ge.ite(rec[None, None, :], X, T, Y, 1, [0.25], ret, 1e-10, 2, want_cov=True, ctx=ctx)
+    so = ge.sate(rec[None, None, :], X, T, Y, 1, [0.25], ret, 1e-10, 2, ctx=ctx)
+    M, Cv = oe.ite_distributions(spec, rec[None, :], X, T, Y, 0.25, 1, 1, 1e-10)
+    assert out["info"].max() == 0
+    assert np.max(np.abs(M - out["mean"][0, 0])) <= 1e-8 * np.max(np.abs(M))
+    assert np.max(np.abs(Cv - out["cov"][0, 0])) <= 1e-8 * np.max(np.abs(Cv))
+    ms, vs = oe.sate_distributions(M, Cv)
+    assert np.allclose(ms, so["mean"][0, 0], rtol=1e-8, atol=1e-12) and np.allclose(vs, so["var"][0, 0], rtol=1e-7)
+
+
 def test_ite_cluster_teams_match_single_cta(ctx, monkeypatch):
     """Team mode (one thread-block cluster per augmented Cholesky, csrc/factor.cuh) only re-partitions the row blocks of a
     panel, so MeanITE, CovITE, info and the draws must be bit-identical to the one-CTA-per-task kernel for every team
