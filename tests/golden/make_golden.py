@@ -56,7 +56,7 @@ kats = {
 if __name__ == "__main__":
     json.dump(kats, open(os.path.join(HERE, "reference_kats.json"), "w"), indent=1)
     for f in ["NEEC_sampled.csv", "IHDP_sampled.csv", "minimal.csv", "no_cov.csv", "no_objects.csv", "no_objects_no_cov.csv",
-              "additive_linear.csv"]:
+              "additive_linear.csv", "additive_nonlinear.csv", "multiplicative_linear.csv", "multiplicative_nonlinear.csv"]:
         shutil.copy(os.path.join(REF, "test", "test_data", f), os.path.join(HERE, "data", f))
     for f in sorted(os.listdir(os.path.join(REF, "test", "test_results"))):
         if f.endswith(".csv"):
