@@ -114,12 +114,11 @@ int gpslc_cov_build(gpslc_ctx* h, int loc, int n, int batch, int D, const double
     GP_TRY(dK.outbuf(loc, K, (size_t)batch * n * n));
     GP_TRY(dw.outbuf(1, nullptr, 0));
     double* w = nullptr;
-    if (D > 0) { GP_CUDA(ctx, cudaMalloc(&w, (size_t)batch * D * sizeof(double))); }
+    if (D > 0) { GP_CUDA(ctx, ctx->arena_alloc(reinterpret_cast<void**>(&w), (size_t)batch * D * sizeof(double))); }
     int rc = launch_inv_sq(ctx, dls.d, w, (size_t)batch * D);
     if (!rc) rc = launch_cov_build(ctx, n, batch, D, df1.d, df2.d, feat_shared ? 0 : (size_t)D * n, w, dsc.d, noise ? dnz.d : nullptr, dK.d);
     if (!rc) rc = dK.finish();
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    if (w) cudaFree(w);
     if (rc) return rc;
     if (e != cudaSuccess) return ctx->cuda_fail(e, "gpslc_cov_build");
     return GPSLC_OK;
@@ -169,7 +168,7 @@ int gpslc_rbf_logpdf(gpslc_ctx* h, int loc, int n, int batch, int D, const doubl
     GP_TRY(dq.outbuf(loc, quad, batch));
     GP_TRY(dinfo.outbuf(loc, info, batch));
     double* w = nullptr;
-    if (D > 0) GP_CUDA(ctx, cudaMalloc(&w, (size_t)batch * D * sizeof(double)));
+    if (D > 0) GP_CUDA(ctx, ctx->arena_alloc(reinterpret_cast<void**>(&w), (size_t)batch * D * sizeof(double)));
     int rc = launch_inv_sq(ctx, dls.d, w, (size_t)batch * D);
     if (!rc) rc = launch_rbf_logpdf(ctx, batch, n, D, df.d, feat_shared ? 0 : (size_t)D * n, w, dsc.d, dnz.d, dy.d, y_shared,
                                     dlp.d, dld.d, dq.d, dinfo.d);
@@ -178,7 +177,6 @@ int gpslc_rbf_logpdf(gpslc_ctx* h, int loc, int n, int batch, int D, const doubl
     if (!rc) rc = dq.finish();
     if (!rc) rc = dinfo.finish();
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    if (w) cudaFree(w);
     if (rc) return rc;
     if (e != cudaSuccess) return ctx->cuda_fail(e, "gpslc_rbf_logpdf");
     return GPSLC_OK;

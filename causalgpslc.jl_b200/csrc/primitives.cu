@@ -72,22 +72,25 @@ __global__ void __launch_bounds__(256) cov_build_kernel(int n, int D, const doub
                                                         size_t feat_stride, const double* __restrict__ w,
                                                         const double* __restrict__ scale, const double* __restrict__ noise,
                                                         int has_noise, double* __restrict__ K) {
-    extern __shared__ double sh[];  // [D] weights, then [D][64] column features, then [D][64*? ] row features
+    // At D = 12 this kernel is bound by the FP64 pipe, not by HBM, unless the per-entry instruction count is kept low: features are
+    // staged pre-scaled by 1 / lengthscale (2 instructions per dimension and entry instead of 3) and the exponential is the
+    // 11-instruction table routine of gens.cuh.
+    extern __shared__ double sh[];  // [32] 2^(i/32) table, then [D][32] column features, then [D][128] row features
     const int b = blockIdx.z;
     const int r0 = blockIdx.x * 128, c0 = blockIdx.y * 32;
-    double* sw = sh;
-    double* sc = sh + D;            // [D][32]  features of the tile's columns (from f2)
-    double* sr = sc + D * 32;       // [D][128] features of the tile's rows (from f1)
+    double* tab = sh;
+    double* sc = sh + 32;           // [D][32]  features of the tile's columns (from f2), times 1 / lengthscale
+    double* sr = sc + D * 32;       // [D][128] features of the tile's rows (from f1), times 1 / lengthscale
     const double* p1 = f1 + (size_t)b * feat_stride;
     const double* p2 = f2 + (size_t)b * feat_stride;
-    for (int i = threadIdx.x; i < D; i += blockDim.x) sw[i] = w[(size_t)b * D + i];
+    if (threadIdx.x < 32) tab[threadIdx.x] = GPSLC_EXP2_TAB[threadIdx.x];
     for (int i = threadIdx.x; i < D * 32; i += blockDim.x) {
         const int d = i >> 5, c = c0 + (i & 31);
-        sc[i] = (c < n) ? p2[(size_t)d * n + c] : 0.0;
+        sc[i] = (c < n) ? p2[(size_t)d * n + c] * sqrt(w[(size_t)b * D + d]) : 0.0;
     }
     for (int i = threadIdx.x; i < D * 128; i += blockDim.x) {
         const int d = i >> 7, r = r0 + (i & 127);
-        sr[i] = (r < n) ? p1[(size_t)d * n + r] : 0.0;
+        sr[i] = (r < n) ? p1[(size_t)d * n + r] * sqrt(w[(size_t)b * D + d]) : 0.0;
     }
     __syncthreads();
     const double s = scale[b];
@@ -100,7 +103,6 @@ __global__ void __launch_bounds__(256) cov_build_kernel(int n, int D, const doub
 #pragma unroll
         for (int i = 0; i < 4; i++) acc[j][i] = 0.0;
     for (int d = 0; d < D; d++) {
-        const double wd = sw[d];
         double zr[4], zc[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) zr[i] = sr[d * 128 + tr + i];
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(256) cov_build_kernel(int n, int D, const doub
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const double t = zr[i] - zc[j];
-                acc[j][i] = fma(t * wd, t, acc[j][i]);
+                acc[j][i] = fma(t, t, acc[j][i]);
             }
     }
     double* Kb = K + (size_t)b * n * n;
@@ -122,8 +124,7 @@ __global__ void __launch_bounds__(256) cov_build_kernel(int n, int D, const doub
         double v[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            v[i] = s * exp(-acc[j][i]);
-            if (has_noise && (r0 + tr + i) == c) v[i] += nz;
+            v[i] = fma(s, exp_neg_tab(acc[j][i], tab), (has_noise && (r0 + tr + i) == c) ? nz : 0.0);
         }
         const int r = r0 + tr;
         double* dst = Kb + (size_t)c * n + r;
@@ -139,10 +140,114 @@ __global__ void __launch_bounds__(256) cov_build_kernel(int n, int D, const doub
     }
 }
 
+// K(X, X): the matrix is symmetric, so only the tiles on and below the block diagonal are computed (half the FP64 work, which is
+// what keeps this kernel off the HBM roofline at D ~ 12) and every off-diagonal tile is written twice, once as it is and once
+// transposed through shared memory so that both stores are coalesced along the fastest (row) dimension. 64 x 64 tiles, one per
+// CTA, 4 x 4 entries per thread. K comes out exactly symmetric.
+__global__ void __launch_bounds__(256) cov_build_sym_kernel(int n, int D, const double* __restrict__ f, size_t feat_stride,
+                                                            const double* __restrict__ w, const double* __restrict__ scale,
+                                                            const double* __restrict__ noise, int has_noise, double* __restrict__ K) {
+    extern __shared__ double sh[];  // [32] 2^(i/32) table, [D][64] column features, [D][64] row features, [64][65] transpose tile
+    const int b = blockIdx.z;
+    // linear index of a lower-triangular tile pair -> (bi >= bj)
+    const int p = blockIdx.x;
+    int bi = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+    while ((bi + 1) * (bi + 2) / 2 <= p) bi++;
+    while (bi * (bi + 1) / 2 > p) bi--;
+    const int bj = p - bi * (bi + 1) / 2;
+    const int r0 = bi * 64, c0 = bj * 64;
+    double* tab = sh;
+    double* sc = sh + 32;
+    double* sr = sc + D * 64;
+    double* tile = sr + D * 64;
+    const double* pf = f + (size_t)b * feat_stride;
+    if (threadIdx.x < 32) tab[threadIdx.x] = GPSLC_EXP2_TAB[threadIdx.x];
+    for (int i = threadIdx.x; i < D * 64; i += blockDim.x) {
+        const int d = i >> 6, o = i & 63;
+        const double sw = sqrt(w[(size_t)b * D + d]);
+        sc[i] = (c0 + o < n) ? pf[(size_t)d * n + c0 + o] * sw : 0.0;
+        sr[i] = (r0 + o < n) ? pf[(size_t)d * n + r0 + o] * sw : 0.0;
+    }
+    __syncthreads();
+    const double s = scale[b];
+    const double nz = has_noise ? noise[b] : 0.0;
+    const int tr = (threadIdx.x & 15) * 4, tc = (threadIdx.x >> 4) * 4;
+    double acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) acc[j][i] = 0.0;
+    for (int d = 0; d < D; d++) {
+        double zr[4], zc[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) zr[i] = sr[d * 64 + tr + i];
+#pragma unroll
+        for (int j = 0; j < 4; j++) zc[j] = sc[d * 64 + tc + j];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const double t = zr[i] - zc[j];
+                acc[j][i] = fma(t, t, acc[j][i]);
+            }
+    }
+    double* Kb = K + (size_t)b * n * n;
+    const bool vec_ok = ((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(Kb) & 31) == 0);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int c = c0 + tc + j;
+        double v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            v[i] = fma(s, exp_neg_tab(acc[j][i], tab), (has_noise && (r0 + tr + i) == c) ? nz : 0.0);
+            tile[(tr + i) * 65 + tc + j] = v[i];
+        }
+        if (c < n) {
+            const int r = r0 + tr;
+            double* dst = Kb + (size_t)c * n + r;
+            if (vec_ok && r + 3 < n) *reinterpret_cast<double4*>(dst) = make_double4(v[0], v[1], v[2], v[3]);
+            else {
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (r + i < n) dst[i] = v[i];
+            }
+        }
+    }
+    if (bi == bj) return;
+    __syncthreads();
+    // transposed tile: output column = a row of this tile, output rows = its columns
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int cc = r0 + tc + j;              // global column of the transposed block (a row index of this tile)
+        if (cc >= n) continue;
+        const int rr = c0 + tr;                  // global rows: the tile's columns
+        double v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) v[i] = tile[(tc + j) * 65 + tr + i];
+        double* dst = Kb + (size_t)cc * n + rr;
+        if (vec_ok && rr + 3 < n) *reinterpret_cast<double4*>(dst) = make_double4(v[0], v[1], v[2], v[3]);
+        else {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (rr + i < n) dst[i] = v[i];
+        }
+    }
+}
+
 int launch_cov_build(Ctx* ctx, int n, int batch, int D, const double* f1, const double* f2, size_t feat_stride,
                      const double* w, const double* scale, const double* noise, double* K) {
+    if (f1 == f2) {
+        const int nt = ceil_div(n, 64);
+        dim3 grid(nt * (nt + 1) / 2, 1, batch);
+        const size_t sh = (size_t)(32 + 2 * D * 64 + 64 * 65) * sizeof(double);
+        GP_CUDA(ctx, cudaFuncSetAttribute(cov_build_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+        cov_build_sym_kernel<<<grid, 256, sh, ctx->stream>>>(n, D, f1, feat_stride, w, scale, noise, noise != nullptr, K);
+        ctx->launches++;
+        GP_CUDA(ctx, cudaGetLastError());
+        return GPSLC_OK;
+    }
     dim3 grid(ceil_div(n, 128), ceil_div(n, 32), batch);
-    size_t sh = (size_t)(D + D * 32 + D * 128) * sizeof(double);
+    size_t sh = (size_t)(32 + D * 32 + D * 128) * sizeof(double);
     cov_build_kernel<<<grid, 256, sh, ctx->stream>>>(n, D, f1, f2, feat_stride, w, scale, noise, noise != nullptr, K);
     ctx->launches++;
     GP_CUDA(ctx, cudaGetLastError());
