@@ -187,7 +187,7 @@ int gpslc_rbf_logpdf(gpslc_ctx* h, int loc, int n, int batch, int D, const doubl
 // ================================================================================================ sampler
 #include "sampler.cuh"
 namespace gpslc {
-int sampler_create(Ctx*, int, int, int, int, int, const double*, const double*, const double*, int, const int*, double, double,
+int sampler_create(Ctx*, int, int, int, int, int, const double*, const double*, const double*, int, const int*, const double*, double, double,
                    const double*, const double*, double, int, int, int, unsigned long long, int, int, int, int, int, Sampler**);
 void sampler_free(Sampler*);
 int sampler_init(Sampler*);
@@ -208,7 +208,7 @@ int gpslc_sampler_create(gpslc_ctx* h, int loc, const gpslc_data* d, const gpslc
     if (!d || !p || !o) return ctx->fail(GPSLC_ERR_ARG, "gpslc_sampler_create: null argument");
     if (o->nOuter < 0 || o->nMHInner < 0 || o->nESInner < 0) return ctx->fail(GPSLC_ERR_ARG, "gpslc_sampler_create: negative iteration count");
     Sampler* s = nullptr;
-    GP_TRY(sampler_create(ctx, loc, d->n, d->nX, d->nU, d->binary, d->X, d->T, d->Y, d->n_obj, d->obj_counts, d->sigma_u_eps,
+    GP_TRY(sampler_create(ctx, loc, d->n, d->nX, d->nU, d->binary, d->X, d->T, d->Y, d->n_obj, d->obj_counts, d->sigma_u_dense, d->sigma_u_eps,
                           d->sigma_u_cov, p->shape, p->scale, p->drift, o->nMHInner, o->nESInner, o->n_chains, o->seed,
                           o->chain_offset, o->u_layout_mode, o->ess_rule, o->observe_x, d->per_chain_data, &s));
     int rc = sampler_init(s);

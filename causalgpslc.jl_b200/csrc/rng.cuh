@@ -47,17 +47,24 @@ struct Stream {
         double u1, u2; uniform_pair(u1, u2);
         return sqrt(-2.0 * log(u1)) * cos(2.0 * 3.14159265358979323846 * u2);
     }
-    // Marsaglia-Tsang, shape >= 1: one normal block + one uniform block per attempt.
+    // Marsaglia-Tsang (2000): one normal block + one uniform block per attempt. Shapes below 1 use the boost
+    // Gamma(a) = Gamma(a + 1) * U^(1/a) (one more uniform block, drawn after the accepted attempt). The rejection loop accepts with
+    // probability > 0.95 per attempt; it is bounded so that a NaN shape can never hang a kernel (the last candidate is returned).
     __host__ __device__ double gamma(double shape) {
-        double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
-        for (;;) {
+        const double a = (shape < 1.0) ? shape + 1.0 : shape;
+        const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+        double g = d;
+        for (int attempt = 0; attempt < 256; attempt++) {
             double x = normal();
             double u = uniform();
             double v = 1.0 + c * x;
             if (v <= 0.0) continue;
             v = v * v * v;
-            if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return d * v;
+            g = d * v;
+            if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) break;
         }
+        if (shape < 1.0) g *= pow(uniform(), 1.0 / shape);
+        return g;
     }
     __host__ __device__ double inv_gamma(double shape, double scale) { return scale / gamma(shape); }
     // element i of the stream's normal vector: block i/2, cosine branch for even i, sine branch for odd i

@@ -53,6 +53,74 @@ __device__ inline double block_u_quad(const ModelDev& m, const double* u, double
     return block_sum(part, red);
 }
 
+// ---- dense (unstructured) SigmaU: `samplePosterior(hyperparams, priorparams, SigmaU, X, T, Y)` accepts any matrix
+// (src/driver.jl:59-69) and generateU factors uNoise*SigmaU (src/model_prior.jl:27-30). Here L_S = chol(SigmaU) is computed once per
+// sampler (m.SL, factor.cuh scratch layout, identity-padded to a multiple of 64); chol(uNoise*SigmaU) = sqrt(uNoise) L_S.
+struct USmem { double red[32]; double wv[NB]; };
+
+// u' SigmaU^-1 u = |L_S^-1 u|^2 by blocked forward substitution; whole CTA of 256 threads; zs: [npad] scratch of this chain
+__device__ inline double dense_u_quad(const ModelDev& m, const double* u, double* zs, USmem& us) {
+    const int NCB = ceil_div(m.n, NB);
+    const int tid = threadIdx.x, r = tid >> 2, kq = tid & 3;
+    __syncthreads();
+    for (int jb = 0; jb < NCB; jb++) {
+        double s = 0.0;
+        for (int J = 0; J < jb; J++) {
+            const double* blk = m.SL + block_off(jb, J, NCB);
+            const double* zj = zs + J * NB;
+            for (int cc = kq; cc < NB; cc += 4) s = fma(blk[elem_off(r, cc)], zj[cc], s);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        const int gi = jb * NB + r;
+        if (kq == 0) us.wv[r] = ((gi < m.n) ? u[gi] : 0.0) - s;
+        __syncthreads();
+        if (tid < 32) {
+            // rows `lane` and `lane + 32` of the 64 x 64 lower-triangular diagonal block
+            const double* blk = m.SL + block_off(jb, jb, NCB);
+            double w0 = us.wv[tid], w1 = us.wv[tid + 32];
+            for (int cc = 0; cc < NB; cc++) {
+                const double wc = __shfl_sync(0xffffffffu, (cc < 32) ? w0 : w1, cc & 31);
+                const double zc = wc / blk[elem_off(cc, cc)];
+                if (tid == (cc & 31)) zs[jb * NB + cc] = zc;
+                if (tid > cc) w0 = fma(-blk[elem_off(tid, cc)], zc, w0);
+                if (tid + 32 > cc) w1 = fma(-blk[elem_off(tid + 32, cc)], zc, w1);
+            }
+        }
+        __syncthreads();
+    }
+    double part = 0.0;
+    for (int i = tid; i < m.n; i += blockDim.x) part = fma(zs[i], zs[i], part);
+    return block_sum(part, us.red);
+}
+
+__device__ inline double u_quad(const ModelDev& m, const ChainDev& c, int chain, const double* u, USmem& us) {
+    if (m.dense_u) return dense_u_quad(m, u, c.zs + (size_t)chain * ceil_div(m.n, NB) * NB, us);
+    return block_u_quad(m, u, us.red);
+}
+
+// out ~ N(0, uNoise*SigmaU) from the normals of stream `st`: block structure sqrt(uNoise) (sqrt(cov) z_obj + sqrt(d) z_i) (exact for the
+// matrix of src/utils.jl:17-33), dense sqrt(uNoise) L_S z. Whole CTA.
+__device__ inline void u_prior_draw(const ModelDev& m, const ChainDev& c, int chain, const Stream& st, double un, double* out) {
+    const double su = sqrt(un);
+    if (m.dense_u) {
+        double* zs = c.zs + (size_t)chain * ceil_div(m.n, NB) * NB;
+        __syncthreads();
+        for (int i = threadIdx.x; i < m.n; i += blockDim.x) zs[i] = st.normal_at(i);
+        __syncthreads();
+        for (int i = threadIdx.x; i < m.n; i += blockDim.x) {
+            double accv[1];
+            tri_matvec_row<1>(m.SL, ceil_div(m.n, NB), 0, 0, i, m.n, zs, 0, 1, accv);
+            out[i] = su * accv[0];
+        }
+        __syncthreads();
+    } else {
+        const double sc = sqrt(m.cov), sd = sqrt(m.dU);
+        for (int i = threadIdx.x; i < m.n; i += blockDim.x)
+            out[i] = su * (sc * st.normal_at(m.n + m.obj_of[i]) + sd * st.normal_at(i));
+    }
+}
+
 // element (r, c) of the n x nU matrix the model's kernels see (src/model_likelihood.jl:7 + src/utils.jl:60-64)
 __device__ __forceinline__ void ueff_src(const ModelDev& m, int r, int c, int& a, int& b) {
     if (m.u_layout_reference) { const long long f = (long long)r + (long long)c * m.n; a = (int)(f % m.nU); b = (int)(f / m.nU); }
@@ -104,7 +172,7 @@ __device__ __forceinline__ double logpdf_from(const FactorOut& o, int n) {
 
 // ------------------------------------------------------------------------------------------------ init (`generate`)
 __global__ void __launch_bounds__(256) init_chains_kernel(ModelDev m, ChainDev c) {
-    __shared__ double red[32];
+    __shared__ USmem us;
     const int chain = blockIdx.x;
     const unsigned gchain = (unsigned)(m.chain0 + chain);
     double* theta = c.theta + (size_t)chain * m.n_params;
@@ -119,10 +187,7 @@ __global__ void __launch_bounds__(256) init_chains_kernel(ModelDev m, ChainDev c
     for (int k = 0; k < m.nU; k++) {
         const double un = theta[0];
         Stream st(m.seed, gchain, (uint32_t)k, stream_b(TAG_INIT_VEC, 0));
-        double* u = c.U + ((size_t)chain * m.nU + k) * m.n;
-        const double su = sqrt(un), sc = sqrt(m.cov), sd = sqrt(m.dU);
-        for (int i = threadIdx.x; i < m.n; i += blockDim.x)
-            u[i] = su * (sc * st.normal_at(m.n + m.obj_of[i]) + sd * st.normal_at(i));
+        u_prior_draw(m, c, chain, st, un, c.U + ((size_t)chain * m.nU + k) * m.n);
     }
     if (m.binary) {
         // logitT ~ N(0, I) when T has no parents (src/model_prior.jl:194-200); with parents init_logit_kernel overwrites it by L z
@@ -141,7 +206,7 @@ __global__ void __launch_bounds__(256) init_chains_kernel(ModelDev m, ChainDev c
     if (m.nU > 0) {
         build_ueff(m, c.U + (size_t)chain * m.nU * m.n, -1, nullptr, c.Ueff + (size_t)chain * m.nU * m.n);
         for (int k = 0; k < m.nU; k++) {
-            const double qv = block_u_quad(m, c.U + ((size_t)chain * m.nU + k) * m.n, red);
+            const double qv = u_quad(m, c, chain, c.U + ((size_t)chain * m.nU + k) * m.n, us);
             if (threadIdx.x == 0) c.q[(size_t)chain * m.nU + k] = qv;
         }
     }
@@ -150,16 +215,28 @@ __global__ void __launch_bounds__(256) init_chains_kernel(ModelDev m, ChainDev c
 
 // recompute the derived per-chain quantities (Ueff, q) after the host overwrote theta/U (gpslc_sampler_set_state)
 __global__ void __launch_bounds__(256) refresh_chains_kernel(ModelDev m, ChainDev c) {
-    __shared__ double red[32];
+    __shared__ USmem us;
     const int chain = blockIdx.x;
     if (m.nU > 0) {
         build_ueff(m, c.U + (size_t)chain * m.nU * m.n, -1, nullptr, c.Ueff + (size_t)chain * m.nU * m.n);
         for (int k = 0; k < m.nU; k++) {
-            const double qv = block_u_quad(m, c.U + ((size_t)chain * m.nU + k) * m.n, red);
+            const double qv = u_quad(m, c, chain, c.U + ((size_t)chain * m.nU + k) * m.n, us);
             if (threadIdx.x == 0) c.q[(size_t)chain * m.nU + k] = qv;
         }
     }
     if (threadIdx.x == 0) c.info[chain] = 0;
+}
+
+// L_S = chol(SigmaU) for a dense SigmaU, once per sampler (one CTA: a start-up cost, not part of any sweep)
+__global__ void __launch_bounds__(FTHREADS, 2) sigma_u_factor_kernel(const double* S, int n, double* SL, double* zbuf, int* info_out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FactorSmem& sm = *reinterpret_cast<FactorSmem*>(smem_raw);
+    factor_smem_init(sm);
+    Pipe pipe{0, 0};
+    const int NCB = ceil_div(n, NB);
+    DenseGen gen{S, {nullptr, nullptr}, n, n};
+    factor_run(gen, NCB, NCB, 0, SL, zbuf, sm, pipe);
+    if (threadIdx.x == 0) *info_out = sm.out.info;
 }
 
 // ------------------------------------------------------------------------------------------------ factor evaluation
@@ -340,7 +417,7 @@ namespace gpslc {
 // ------------------------------------------------------------------------------------------------ ESS over U_k
 constexpr int ESS_MAX_EVALS = 200;
 // ess[c][0..4] = log u, theta, theta_min, theta_max, next scalar-stream block
-__device__ inline void ess_make_proposal(const ModelDev& m, const ChainDev& c, int chain, int k, double th, double* red) {
+__device__ inline void ess_make_proposal(const ModelDev& m, const ChainDev& c, int chain, int k, double th, USmem& us) {
     const double* u = c.U + ((size_t)chain * m.nU + k) * m.n;
     const double* nu = c.nu + (size_t)chain * m.n;
     double* up = c.Uprop + (size_t)chain * m.n;
@@ -348,21 +425,18 @@ __device__ inline void ess_make_proposal(const ModelDev& m, const ChainDev& c, i
     for (int i = threadIdx.x; i < m.n; i += blockDim.x) up[i] = u[i] * cs + nu[i] * sn;
     __syncthreads();
     build_ueff(m, c.U + (size_t)chain * m.nU * m.n, k, up, c.UeffP + (size_t)chain * m.nU * m.n);
-    const double qv = block_u_quad(m, up, red);
+    const double qv = u_quad(m, c, chain, up, us);
     if (threadIdx.x == 0) { c.qP[chain] = qv; c.infoP[chain] = 0; }
 }
 
 __global__ void __launch_bounds__(256) ess_begin_kernel(ModelDev m, ChainDev c, int k, uint32_t it) {
-    __shared__ double red[32];
+    __shared__ USmem us;
     __shared__ double s_th;
     const int chain = blockIdx.x;
     const unsigned gchain = (unsigned)(m.chain0 + chain);
     const double un = c.theta[(size_t)chain * m.n_params + 0];
     Stream sn(m.seed, gchain, (uint32_t)k, stream_b(TAG_ESS_NU, it));
-    double* nu = c.nu + (size_t)chain * m.n;
-    const double su = sqrt(un), sc = sqrt(m.cov), sd = sqrt(m.dU);
-    for (int i = threadIdx.x; i < m.n; i += blockDim.x)
-        nu[i] = su * (sc * sn.normal_at(m.n + m.obj_of[i]) + sd * sn.normal_at(i));
+    u_prior_draw(m, c, chain, sn, un, c.nu + (size_t)chain * m.n);
     if (threadIdx.x == 0) {
         Stream ss(m.seed, gchain, (uint32_t)k, stream_b(TAG_ESS_SCALAR, it));
         double u, v;
@@ -375,12 +449,12 @@ __global__ void __launch_bounds__(256) ess_begin_kernel(ModelDev m, ChainDev c, 
         if (chain == 0) { c.n_active[0] = gridDim.x; c.n_active[1] = 0; }
     }
     __syncthreads();
-    ess_make_proposal(m, c, chain, k, s_th, red);
+    ess_make_proposal(m, c, chain, k, s_th, us);
 }
 
 __global__ void __launch_bounds__(256) ess_decide_kernel(ModelDev m, ChainDev c, int k, uint32_t it, const int* list_in,
                                                          int* list_out, unsigned int* n_out, const int* exist, int n_exist) {
-    __shared__ double red[32];
+    __shared__ USmem us;
     __shared__ double s_th;
     __shared__ int s_accept;
     const int chain = list_in[blockIdx.x];
@@ -429,7 +503,7 @@ __global__ void __launch_bounds__(256) ess_decide_kernel(ModelDev m, ChainDev c,
         }
         if (threadIdx.x == 0) c.q[(size_t)chain * m.nU + k] = c.qP[chain];
     } else {
-        ess_make_proposal(m, c, chain, k, s_th, red);
+        ess_make_proposal(m, c, chain, k, s_th, us);
     }
 }
 
@@ -559,7 +633,9 @@ ess_logit_kernel(ModelDev m, ChainDev c, int jj, uint32_t it, double* scratch, s
             if (threadIdx.x == 0) {
                 evals++;
                 quad = cs * cs * o.gram[0] + 2.0 * sn * cs * o.gram[1] + sn * sn * o.gram[2];
-                const double w = -0.5 * (quad - o.gram[0]) + (bern - bern0);
+                // ess_rule 0: Gen's full `update` weight = change of the N(0, K_T) term at :logitT + change of the Bernoulli terms;
+                // ess_rule 1: textbook slice test on the likelihood (the Bernoulli terms) only — same switch as for the U_k
+                const double w = (m.ess_rule == 0 ? -0.5 * (quad - o.gram[0]) : 0.0) + (bern - bern0);
                 if (!(w <= logu) || evals >= ESS_MAX_EVALS) {
                     s_done = 1;
                 } else {
@@ -648,15 +724,22 @@ void sampler_free(Sampler* s) {
 
 // Build every table. data pointers are host pointers (loc==0) or device pointers (loc==1).
 int sampler_create(Ctx* ctx, int loc, int n, int nX, int nU, int binary, const double* X, const double* T, const double* Y,
-                   int n_obj, const int* obj_counts, double eps, double cov, const double* pshape, const double* pscale,
+                   int n_obj, const int* obj_counts, const double* sigma_dense, double eps, double cov, const double* pshape, const double* pscale,
                    double drift, int nMH, int nES, int n_chains, unsigned long long seed, int chain_offset, int u_layout_mode,
                    int ess_rule, int observe_x, int per_chain_data, Sampler** out) {
     *out = nullptr;
     if (n <= 0 || nX < 0 || nU < 0 || n_chains <= 0 || !T || !Y || (nX > 0 && !X)) return ctx->fail(GPSLC_ERR_ARG, "sampler_create: bad argument");
     if (nU + nX + 1 > DMAX) return ctx->fail(GPSLC_ERR_UNSUPPORTED, "sampler_create: nU + nX + 1 exceeds DMAX");
     const bool has_u = nU > 0, has_x = nX > 0;
-    if (has_u) {
-        if (n_obj <= 0 || !obj_counts) return ctx->fail(GPSLC_ERR_ARG, "sampler_create: nU > 0 needs the object counts of SigmaU");
+    // InvGamma(shape, scale) priors and the proposal variance must be positive and finite (Distributions.InverseGamma throws
+    // an ArgumentError otherwise); a bad value would otherwise reach the gamma sampler inside a kernel
+    for (int fam = 0; fam < P_NFAM; fam++)
+        if (!(pshape[fam] > 0.0) || !(pscale[fam] > 0.0) || !(pshape[fam] < 1e300) || !(pscale[fam] < 1e300))
+            return ctx->fail(GPSLC_ERR_ARG, "sampler_create: InvGamma prior shape and scale must be positive and finite (family " + std::to_string(fam) + ")");
+    if (!(drift > 0.0) || !(drift < 1e300)) return ctx->fail(GPSLC_ERR_ARG, "sampler_create: drift (proposal variance) must be positive and finite");
+    const bool dense_u = has_u && sigma_dense != nullptr && (n_obj <= 0 || !obj_counts);
+    if (has_u && !dense_u) {
+        if (n_obj <= 0 || !obj_counts) return ctx->fail(GPSLC_ERR_ARG, "sampler_create: nU > 0 needs SigmaU: its object counts, or the dense matrix");
         long long tot = 0;
         for (int o = 0; o < n_obj; o++) { if (obj_counts[o] <= 0) return ctx->fail(GPSLC_ERR_ARG, "sampler_create: non-positive object count"); tot += obj_counts[o]; }
         if (tot != n) return ctx->fail(GPSLC_ERR_ARG, "sampler_create: object counts do not sum to n");
@@ -677,7 +760,9 @@ int sampler_create(Ctx* ctx, int loc, int n, int nX, int nU, int binary, const d
     m.seed = seed; m.chain0 = chain_offset; m.n_chains = n_chains;
     m.nMH = (!has_u && !has_x) ? 1 : nMH;   // inference.jl:157-160: three sites once per outer iteration
     m.nES = nES;
-    m.n_obj = has_u ? n_obj : 0;
+    m.n_obj = (has_u && !dense_u) ? n_obj : 0;
+    m.dense_u = dense_u ? 1 : 0;
+    m.SL = nullptr;
 
     // ---- factor table (src/model_likelihood.jl)
     s->h_fdef.assign(m.nF, FactorDef{});
@@ -813,6 +898,7 @@ int sampler_create(Ctx* ctx, int loc, int n, int nX, int nU, int binary, const d
     S_TRY(dev_alloc(s, &c.ess_evals, C));
     S_TRY(dev_alloc(s, &c.ess_evals_logit, C));
     S_TRY(dev_alloc(s, &c.nuL, binary ? C * (size_t)(nES > 0 ? nES : 1) * n : 1));
+    S_TRY(dev_alloc(s, &c.zs, dense_u ? C * (size_t)ceil_div(n, NB) * NB : 1));
     cudaMemsetAsync(c.lp, 0, C * m.nF * sizeof(double), ctx->stream);
     cudaMemsetAsync(c.lpP, 0, C * m.nF * sizeof(double), ctx->stream);
     cudaMemsetAsync(c.accepts, 0, C * m.n_sites * sizeof(unsigned long long), ctx->stream);
@@ -822,6 +908,23 @@ int sampler_create(Ctx* ctx, int loc, int n, int nX, int nU, int binary, const d
     cudaMemsetAsync(c.infoP, 0, C * sizeof(int), ctx->stream);
     const int NCB = ceil_div(n, NB);
     { int g0 = 0; S_TRY(ensure_workspace(ctx, NCB, NCB, (long long)n_chains * (nX + 2), &g0)); }
+    if (dense_u) {
+        // SigmaU -> device (host pointer unless loc == 1), factor once; a non-PD SigmaU is the PosDefException generateU would throw
+        const double* dS = sigma_dense;
+        if (loc != 1) { double* t; S_TRY(dev_alloc(s, &t, (size_t)n * n)); cudaMemcpyAsync(t, sigma_dense, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream); dS = t; }
+        double* SL; int* dinfo;
+        S_TRY(dev_alloc(s, &SL, scratch_doubles(NCB, NCB)));
+        S_TRY(dev_alloc(s, &dinfo, 1));
+        cudaFuncSetAttribute(sigma_u_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem));
+        sigma_u_factor_kernel<<<1, FTHREADS, sizeof(FactorSmem), ctx->stream>>>(dS, n, SL, ctx->zbuf, dinfo);
+        ctx->launches++;
+        int hinfo = 0;
+        cudaError_t e1 = cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) { sampler_free(s); return ctx->cuda_fail(e1 != cudaSuccess ? e1 : e2, "sigma_u_factor_kernel"); }
+        if (hinfo != 0) { sampler_free(s); return ctx->fail(GPSLC_ERR_NOT_PD, "SigmaU is not positive definite (leading minor " + std::to_string(hinfo) + ")"); }
+        m.SL = SL;
+    }
 #undef S_TRY
     *out = s;
     return GPSLC_OK;

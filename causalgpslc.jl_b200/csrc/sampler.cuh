@@ -44,11 +44,14 @@ struct ModelDev {
     unsigned long long seed;
     int chain0, n_chains;
     int nMH, nES;
+    int dense_u;                    // SigmaU is an unstructured dense matrix: SL holds its Cholesky factor (factor.cuh scratch layout)
+    const double* SL;
     int ls_unsquared;               // experiment knob (GPSLC_LS_UNSQUARED=1): kernel exp(-d^2 / ls) instead of exp(-d^2 / ls^2), see DESIGN.md §5
 };
 
 struct ChainDev {
     double *theta, *U, *Ueff, *UeffP, *Uprop, *nu, *lp, *lpP, *q, *qP, *ess, *logitT, *Xmodel;
+    double* zs;                     // dense SigmaU: [C][npad] forward-solve / normal-draw scratch
     double* nuL;                    // binary T: [C][nES][n] slice directions L_stale z_j drawn once per outer iteration (App. B6)
     int *info, *infoP;
     int *active_a, *active_b;       // double-buffered compacted lists of chains still slicing

@@ -23,6 +23,25 @@ class GpslcError(RuntimeError):
         self.code = code
 
 
+class PosDefException(GpslcError, ArithmeticError):
+    """The analogue of Julia's LinearAlgebra.PosDefException(info): a covariance the reference would hand to `cholesky`
+    (Kp in src/likelihood.jl:42-43, CovITE in the `mvnormal` draw of src/estimation.jl:105) is not positive definite."""
+
+    def __init__(self, info, where):
+        GpslcError.__init__(self, 3, f"matrix is not positive definite; Cholesky factorization failed (leading minor {info}) in {where}")
+        self.info = int(info)
+
+
+def check_info(info, what, doT=None):
+    """Raise PosDefException for the first non-zero entry of a [doT][chain][sample] info array (the reference aborts the whole
+    sampleITE / sampleSATE call with a PosDefException in that case; the library reports it per task and carries on)."""
+    bad = np.argwhere(np.asarray(info) != 0)
+    if bad.size:
+        d, c, r = (int(x) for x in bad[0])
+        where = f"{what}: doT index {d}" + (f" (doT = {np.atleast_1d(doT)[d]})" if doT is not None else "") + f", chain {c}, retained sample {r}"
+        raise PosDefException(int(np.asarray(info)[d, c, r]), where + f"; {len(bad)} of {np.asarray(info).size} tasks failed")
+
+
 def load():
     """Load the shared library (no GPU needed for this step)."""
     global _lib

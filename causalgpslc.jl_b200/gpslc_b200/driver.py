@@ -4,7 +4,8 @@ import copy
 
 import numpy as np
 
-from .data import prepareData
+from ._lib import check_info
+from .data import prepareData, objectCounts
 from .estimation import ite as _ite, sate as _sate, retained_indices
 from .hyperparameters import getHyperParameters, getPriorParameters
 from .inference import Posterior
@@ -48,13 +49,13 @@ def gpslc(*args, hyperparams=None, priorparams=None, n_chains=1, seed=0, ctx=Non
     hyperparams = copy.copy(hyperparams) if hyperparams is not None else getHyperParameters()
     priorparams = priorparams if priorparams is not None else getPriorParameters()
     if len(args) == 1:
-        SigmaU, obj, X, T, Y, counts = prepareData(args[0])
+        SigmaU, obj, X, T, Y = prepareData(args[0])     # default eps / cov, whatever priorparams says (src/driver.jl:31)
+        counts = None                                   # the structure (counts, eps, cov) is read off SigmaU itself
     elif len(args) == 4:
         obj, X, T, Y = args
         counts = None
         if obj is not None:
-            counts = [int(c) for c in obj]
-            SigmaU = generateSigmaU(counts, priorparams["sigmaUNoise"], priorparams["sigmaUCov"])
+            SigmaU = generateSigmaU([int(c) for c in obj], priorparams["sigmaUNoise"], priorparams["sigmaUCov"])
         else:
             SigmaU = None
     else:
@@ -71,6 +72,7 @@ def ITEDistributions(g, doT, ctx=None):
     """src/estimation.jl:66-86 -> (MeanITEs [R, n], CovITEs [R, n, n]) for chain 0."""
     o = _ite(g.posteriorPacked[:, :1], g.X, g.T, g.Y, g.hyperparams.nU, float(doT), _ret(g),
              g.hyperparams.predictionCovarianceNoise, 0, want_cov=True, want_samples=False, ctx=ctx)
+    check_info(o["info"], "ITEDistributions", doT)
     return o["mean"][0, 0], o["cov"][0, 0]
 
 
@@ -79,6 +81,7 @@ def sampleITE(g, doT, samplesPerPosterior=10, all_chains=False, ctx=None):
     packed = g.posteriorPacked if all_chains else g.posteriorPacked[:, :1]
     o = _ite(packed, g.X, g.T, g.Y, g.hyperparams.nU, float(doT), _ret(g), g.hyperparams.predictionCovarianceNoise,
              samplesPerPosterior, seed=g.seed, ctx=ctx)
+    check_info(o["info"], "sampleITE", doT)
     s = np.swapaxes(o["samples"][0], 1, 2)          # [C, n, R*spp]
     return s if all_chains else s[0]
 
@@ -87,6 +90,7 @@ def SATEDistributions(g, doT, ctx=None):
     """src/estimation.jl:127-140 -> (MeanSATEs [R], VarSATEs [R])."""
     o = _sate(g.posteriorPacked[:, :1], g.X, g.T, g.Y, g.hyperparams.nU, float(doT), _ret(g),
               g.hyperparams.predictionCovarianceNoise, 0, ctx=ctx)
+    check_info(o["info"], "SATEDistributions", doT)
     return o["mean"][0, 0], o["var"][0, 0]
 
 
@@ -95,6 +99,7 @@ def sampleSATE(g, doT, samplesPerPosterior=10, all_chains=False, var_as_std=True
     packed = g.posteriorPacked if all_chains else g.posteriorPacked[:, :1]
     o = _sate(packed, g.X, g.T, g.Y, g.hyperparams.nU, float(doT), _ret(g), g.hyperparams.predictionCovarianceNoise,
               samplesPerPosterior, seed=g.seed, var_as_std=var_as_std, ctx=ctx)
+    check_info(o["info"], "sampleSATE", doT)
     return o["samples"][0] if all_chains else o["samples"][0, 0]
 
 

@@ -15,7 +15,8 @@ class GpslcData(ctypes.Structure):
     _fields_ = [("n", ctypes.c_int), ("nX", ctypes.c_int), ("nU", ctypes.c_int), ("binary", ctypes.c_int),
                 ("X", ctypes.c_void_p), ("T", ctypes.c_void_p), ("Y", ctypes.c_void_p),
                 ("n_obj", ctypes.c_int), ("obj_counts", ctypes.c_void_p),
-                ("sigma_u_eps", ctypes.c_double), ("sigma_u_cov", ctypes.c_double), ("per_chain_data", ctypes.c_int)]
+                ("sigma_u_eps", ctypes.c_double), ("sigma_u_cov", ctypes.c_double), ("per_chain_data", ctypes.c_int),
+                ("sigma_u_dense", ctypes.c_void_p)]
 
 
 class GpslcPrior(ctypes.Structure):
@@ -59,29 +60,57 @@ def _bind(lib):
     lib._sampler_bound = True
 
 
-def sigma_u_to_counts(SigmaU, eps, cov):
-    """Recover the object counts from a dense SigmaU built by generateSigmaU (src/utils.jl:17-33). The CUDA path uses
-    the closed form of that block structure; any other SigmaU is rejected loudly (no dense fallback in this build)."""
+def sigma_u_structure(SigmaU):
+    """Detect the block structure generateSigmaU produces (src/utils.jl:17-33) in a dense SigmaU: identity with every object's
+    block set to one common `cov` and the whole diagonal to one common value 1 + eps. Returns (counts, eps, cov) with
+    fl(1 + eps) == the diagonal value exactly, or None when the matrix is anything else (the library then factors it densely,
+    like the reference's generateU does, src/model_prior.jl:27-30)."""
     S = np.asarray(SigmaU, dtype=np.float64)
     n = S.shape[0]
-    counts = []
-    i = 0
+    if S.ndim != 2 or S.shape != (n, n):
+        raise ValueError("SigmaU must be a square matrix")
+    diag = S[0, 0]
+    if not np.all(np.diagonal(S) == diag):
+        return None
+    counts, cov, i = [], None, 0
     while i < n:
         j = i + 1
         while j < n and S[i, j] != 0.0:
             j += 1
+        if j - i > 1:
+            if cov is None:
+                cov = S[i, i + 1]
+            elif S[i, i + 1] != cov:
+                return None
         counts.append(j - i)
         i = j
+    cov = 0.0 if cov is None else float(cov)
+    R = np.zeros((n, n))
+    i = 0
+    for m in counts:
+        R[i:i + m, i:i + m] = cov
+        i += m
+    R[np.diag_indices(n)] = diag
+    if not np.array_equal(R, S) or not (diag - cov > 0.0) or not (cov >= 0.0):
+        return None
+    return counts, float(diag - 1.0), cov
+
+
+def sigma_u_to_counts(SigmaU, eps, cov):
+    """Object counts of a SigmaU built by generateSigmaU(counts, eps, cov); ValueError for anything else."""
+    st = sigma_u_structure(SigmaU)
     from .utils import generateSigmaU
-    if not np.array_equal(generateSigmaU(counts, eps, cov), S):
-        raise ValueError("SigmaU is not the block matrix generateSigmaU(counts, sigmaUNoise, sigmaUCov) produces; "
-                         "the B200 path supports only that structure")
-    return counts
+    if st is None or not np.array_equal(generateSigmaU(st[0], eps, cov), np.asarray(SigmaU, dtype=np.float64)):
+        raise ValueError("SigmaU is not the block matrix generateSigmaU(counts, sigmaUNoise, sigmaUCov) produces")
+    return st[0]
 
 
 def make_structs(priorparams, X, T, Y, nU, counts, nOuter, nMHInner, nESInner, n_chains, seed, chain_offset,
                  u_layout_mode, ess_rule, observe_x, per_chain_data=False):
-    """per_chain_data: T, Y are [n_chains, n] and X is [n_chains, n, nX] (one dataset per chain)."""
+    """per_chain_data: T, Y are [n_chains, n] and X is [n_chains, n, nX] (one dataset per chain).
+    counts: object counts of a block-structured SigmaU (with priorparams["sigmaUNoise"], ["sigmaUCov"] as its eps / cov), or
+    None: priorparams["SigmaU"] is analysed — block matrices go to the closed-form path with the eps / cov found IN the matrix,
+    anything else is handed over densely (gpslc_data.sigma_u_dense)."""
     T = np.asarray(T)
     binary = T.dtype == np.bool_
     keep = {}
@@ -99,13 +128,23 @@ def make_structs(priorparams, X, T, Y, nU, counts, nOuter, nMHInner, nESInner, n
     d.X = keep["X"].ctypes.data if nX else None
     d.T = keep["T"].ctypes.data
     d.Y = keep["Y"].ctypes.data
-    if nU:
-        keep["counts"] = np.ascontiguousarray(counts, dtype=np.int32)
-        d.n_obj = len(counts)
-        d.obj_counts = keep["counts"].ctypes.data
-    d.per_chain_data = int(bool(per_chain_data))
     d.sigma_u_eps = float(priorparams["sigmaUNoise"])
     d.sigma_u_cov = float(priorparams["sigmaUCov"])
+    if nU:
+        if counts is None:
+            st = sigma_u_structure(priorparams["SigmaU"])
+            if st is not None:
+                counts, d.sigma_u_eps, d.sigma_u_cov = st
+            else:
+                keep["SigmaU"] = np.asfortranarray(priorparams["SigmaU"], dtype=np.float64)
+                if keep["SigmaU"].shape != (n, n):
+                    raise ValueError("SigmaU must be n x n")
+                d.sigma_u_dense = keep["SigmaU"].ctypes.data
+        if counts is not None:
+            keep["counts"] = np.ascontiguousarray(counts, dtype=np.int32)
+            d.n_obj = len(counts)
+            d.obj_counts = keep["counts"].ctypes.data
+    d.per_chain_data = int(bool(per_chain_data))
     p = GpslcPrior()
     for k, fam in enumerate(PRIOR_FAMILIES):
         p.shape[k] = float(priorparams[fam + "Shape"])
@@ -196,11 +235,7 @@ def Posterior(priorparams, X, T, Y, nU, nOuter, nMHInner, nESInner, n_chains=1, 
     """`Posterior(priorparams, X, T, Y, nU, nOuter, nMHInner, nESInner)` (src/inference.jl:4-379; dispatch on
     `X === nothing`, `nU === nothing` and the element type of T picks one of the eight methods). priorparams must carry
     "SigmaU" when nU is not None (src/driver.jl:61). Returns the packed samples [nOuter, n_chains, stride]."""
-    counts = None
-    if nU:
-        counts = priorparams.get("_obj_counts")
-        if counts is None:
-            counts = sigma_u_to_counts(priorparams["SigmaU"], priorparams["sigmaUNoise"], priorparams["sigmaUCov"])
+    counts = priorparams.get("_obj_counts") if nU else None      # None: make_structs analyses priorparams["SigmaU"]
     s = ChainSampler(priorparams, X, T, Y, nU, counts, nOuter, nMHInner, nESInner, n_chains, seed, chain_offset,
                      u_layout_mode, ess_rule, observe_x, ctx)
     try:

@@ -3,6 +3,7 @@ per doT (re-extracting parameters and re-factorising every time, SURVEY.md §3.5
 one gpslc_ite call."""
 import numpy as np
 
+from ._lib import check_info
 from .driver import _ret
 from .estimation import ite as _ite
 from .utils import getN, getNumPosteriorSamples
@@ -20,6 +21,7 @@ def predictCounterfactualEffects(g, nSamplesPerMixture, fidelity=100, minDoT=Non
     off, cnt = shard_chains(len(doTrange), world_size, rank)
     o = _ite(g.posteriorPacked[:, :1], g.X, g.T, g.Y, g.hyperparams.nU, doTrange[off:off + cnt], _ret(g),
              g.hyperparams.predictionCovarianceNoise, nSamplesPerMixture, seed=g.seed, ctx=ctx, dot_offset=off)
+    check_info(o["info"], "predictCounterfactualEffects", doTrange[off:off + cnt])
     ite = np.swapaxes(o["samples"][:, 0], 1, 2)               # [d_local, n, R*spp]
     assert ite.shape == (cnt, getN(g), getNumPosteriorSamples(g) * nSamplesPerMixture)
     return ite, doTrange

@@ -9,6 +9,8 @@
 module CausalGPSLCB200
 
 using Gen
+using LinearAlgebra      # PosDefException
+using Random             # default seeds come from Julia's global RNG, so Random.seed!(...) keeps working as in the reference
 
 const LIB = Ref{String}("libgpslc_b200.so")
 const CTX = Ref{Ptr{Cvoid}}(C_NULL)
@@ -19,6 +21,7 @@ struct GpslcData            # include/gpslc.h: gpslc_data
     n_obj::Cint; obj_counts::Ptr{Cint}
     sigma_u_eps::Cdouble; sigma_u_cov::Cdouble
     per_chain_data::Cint
+    sigma_u_dense::Ptr{Cdouble}
 end
 struct GpslcPrior           # gpslc_prior
     shape::NTuple{13,Cdouble}; scale::NTuple{13,Cdouble}; drift::Cdouble
@@ -37,6 +40,12 @@ function check(rc::Cint)
     error("gpslc error $rc: $msg")
 end
 
+"per-task LAPACK-style info of gpslc_ite / gpslc_sate: the reference aborts with PosDefException when Kp or CovITE is not PD"
+function check_info(info::Vector{Cint})
+    k = findfirst(!=(0), info)
+    k === nothing || throw(LinearAlgebra.PosDefException(Int(info[k])))
+end
+
 function init!(libpath::String=LIB[]; device::Int=0)
     LIB[] = libpath
     h = Ref{Ptr{Cvoid}}(C_NULL)
@@ -45,15 +54,30 @@ function init!(libpath::String=LIB[]; device::Int=0)
     CTX[] = h[]
 end
 
-"object counts of a SigmaU built by generateSigmaU (src/utils.jl:17-33); anything else is rejected"
-function sigmaUcounts(SigmaU::Matrix{Float64})
+"""
+Block structure of a SigmaU built by generateSigmaU (src/utils.jl:17-33): (counts, eps, cov) with 1 + eps == the common diagonal
+value and `cov` the common within-object entry, or `nothing` for any other matrix (which is then passed densely: the library factors
+it once, as generateU's `mvnormal` would on every update, src/model_prior.jl:27-30).
+"""
+function sigmaUstructure(SigmaU::Matrix{Float64})
     n = size(SigmaU, 1); counts = Cint[]; i = 1
+    dg = SigmaU[1, 1]; cov = nothing
+    all(SigmaU[k, k] == dg for k in 1:n) || return nothing
     while i <= n
         j = i + 1
         while j <= n && SigmaU[i, j] != 0.0; j += 1; end
+        if j - i > 1
+            c = SigmaU[i, i+1]
+            cov === nothing ? (cov = c) : (c == cov || return nothing)
+        end
         push!(counts, j - i); i = j
     end
-    counts
+    cov = cov === nothing ? 0.0 : cov
+    R = zeros(n, n); i = 1
+    for m in counts; R[i:i+m-1, i:i+m-1] .= cov; i += m; end
+    for k in 1:n; R[k, k] = dg; end
+    (R == SigmaU && dg - cov > 0 && cov >= 0) || return nothing
+    counts, dg - 1.0, cov
 end
 
 prior_struct(pp) = GpslcPrior(ntuple(k -> Float64(pp[FAMILIES[k] * "Shape"]), 13),
@@ -89,21 +113,29 @@ end
 """
     Posterior(priorparams, X, T, Y, nU, nOuter, nMHInner, nESInner)
 Replaces all eight methods of src/inference.jl:4-379 (called from samplePosterior, src/driver.jl:59-69).
-Returns (posteriorSamples::Vector{Any} of choicemaps, packed::Array{Float64,3}) — the reference returns the final trace as
-second value, which samplePosterior discards (src/driver.jl:62).
+Returns (posteriorSamples::Vector{Any} of choicemaps, packed::Array{Float64,3}).
+DEVIATION from the reference, on purpose: the reference returns `(samples, trace)` (src/inference.jl:58); no Gen trace exists on
+the GPU path, so the second value is the packed sample buffer [stride, n_chains, nOuter] instead. Its only caller,
+samplePosterior (src/driver.jl:62), discards it.
+`seed` defaults to a draw from Julia's global RNG: like the reference, repeated calls give different chains and
+`Random.seed!(1234)` (test/runtests.jl:18) makes a run reproducible.
 """
-function Posterior(priorparams, X, T, Y, nU, nOuter, nMHInner, nESInner; n_chains=1, seed=UInt64(0), chain_offset=0,
+function Posterior(priorparams, X, T, Y, nU, nOuter, nMHInner, nESInner; n_chains=1, seed=rand(UInt64), chain_offset=0,
                    u_layout_mode=0, ess_rule=0, observe_x=0)
     n = length(Y); nX = X === nothing ? 0 : size(X, 2); nu = nU === nothing ? 0 : nU
     binary = eltype(T) == Bool
     Tf = Float64.(T); Xf = X === nothing ? Float64[] : Matrix{Float64}(X); Yf = Float64.(Y)
-    counts = nu > 0 ? sigmaUcounts(priorparams["SigmaU"]) : Cint[]
+    st = nu > 0 ? sigmaUstructure(Matrix{Float64}(priorparams["SigmaU"])) : nothing
+    counts = st === nothing ? Cint[] : st[1]
+    eps_u = st === nothing ? Float64(priorparams["sigmaUNoise"]) : st[2]
+    cov_u = st === nothing ? Float64(priorparams["sigmaUCov"]) : st[3]
+    Sd = (nu > 0 && st === nothing) ? Matrix{Float64}(priorparams["SigmaU"]) : zeros(0, 0)     # unstructured SigmaU: dense path
     np = 6 + 4nX + 2nu + nu * nX
     stride = np + nu * n + (binary ? n : 0) + ((nu == 0 && nX > 0 && observe_x == 0) ? n * nX : 0)
     out = Array{Float64}(undef, stride, n_chains, nOuter)          # column-major == C [nOuter][n_chains][stride]
-    GC.@preserve Tf Xf Yf counts out begin
+    GC.@preserve Tf Xf Yf counts Sd out begin
         d = GpslcData(n, nX, nu, binary, nX > 0 ? pointer(Xf) : C_NULL, pointer(Tf), pointer(Yf), length(counts),
-                      nu > 0 ? pointer(counts) : C_NULL, priorparams["sigmaUNoise"], priorparams["sigmaUCov"], 0)
+                      length(counts) > 0 ? pointer(counts) : C_NULL, eps_u, cov_u, 0, length(Sd) > 0 ? pointer(Sd) : C_NULL)
         o = GpslcOpts(nOuter, something(nMHInner, 0), something(nESInner, 0), n_chains, seed, chain_offset, u_layout_mode, ess_rule, observe_x)
         check(ccall((:gpslc_posterior, LIB[]), Cint,
                     (Ptr{Cvoid}, Ref{GpslcData}, Ref{GpslcPrior}, Ref{GpslcOpts}, Ptr{Cdouble}, Ptr{Culonglong}, Ptr{Culonglong}),
@@ -133,25 +165,26 @@ end
 
 function data_struct(g, Tf, Xf, Yf)
     nX = g.X === nothing ? 0 : size(g.X, 2); nU = g.hyperparams.nU === nothing ? 0 : g.hyperparams.nU
-    GpslcData(length(Yf), nX, nU, eltype(g.T) == Bool, nX > 0 ? pointer(Xf) : C_NULL, pointer(Tf), pointer(Yf), 0, C_NULL, 0.0, 0.0, 0)
+    GpslcData(length(Yf), nX, nU, eltype(g.T) == Bool, nX > 0 ? pointer(Xf) : C_NULL, pointer(Tf), pointer(Yf), 0, C_NULL, 0.0, 0.0, 0, C_NULL)
 end
 
 """
     sampleITE(g, doT; samplesPerPosterior=10)   — replaces src/driver.jl:86-89 (ITEDistributions + ITEsamples,
 src/estimation.jl:66-109, likelihoodDistribution src/likelihood.jl:8-174). Returns n × (R*samplesPerPosterior).
 """
-function sampleITE(g, doT; samplesPerPosterior::Int=10, seed=UInt64(0))
+function sampleITE(g, doT; samplesPerPosterior::Int=10, seed=rand(UInt64))
     packed = pack(g); ret = retained(g.hyperparams); R = length(ret); n = length(g.Y)
     Tf = Float64.(g.T); Xf = g.X === nothing ? Float64[] : Matrix{Float64}(g.X); Yf = Float64.(g.Y)
     out = Array{Float64}(undef, n, R * samplesPerPosterior)
-    dts = Float64[doT]
-    GC.@preserve packed ret Tf Xf Yf out dts begin
+    dts = Float64[doT]; info = zeros(Cint, R)
+    GC.@preserve packed ret Tf Xf Yf out dts info begin
         check(ccall((:gpslc_ite, LIB[]), Cint,
                     (Ptr{Cvoid}, Cint, Ref{GpslcData}, Ptr{Cdouble}, Cint, Cint, Cint, Ptr{Cint}, Cint, Ptr{Cdouble}, Cint, Cdouble,
                      Cint, UInt64, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cint}),
                     CTX[], 0, data_struct(g, Tf, Xf, Yf), packed, size(packed, 3), 1, size(packed, 1), ret, R, dts, 1,
-                    g.hyperparams.predictionCovarianceNoise, samplesPerPosterior, seed, 0, C_NULL, C_NULL, out, C_NULL))
+                    g.hyperparams.predictionCovarianceNoise, samplesPerPosterior, seed, 0, C_NULL, C_NULL, out, info))
     end
+    check_info(info)
     out
 end
 
@@ -159,18 +192,19 @@ end
     sampleSATE(g, doT; samplesPerPosterior=10)  — replaces src/driver.jl:108-111 (SATEDistributions + SATEsamples,
 src/estimation.jl:116-163). var_as_std=1 keeps the reference's `normal(mean, var)` behaviour.
 """
-function sampleSATE(g, doT; samplesPerPosterior::Int=10, seed=UInt64(0), var_as_std::Int=1)
+function sampleSATE(g, doT; samplesPerPosterior::Int=10, seed=rand(UInt64), var_as_std::Int=1)
     packed = pack(g); ret = retained(g.hyperparams); R = length(ret)
     Tf = Float64.(g.T); Xf = g.X === nothing ? Float64[] : Matrix{Float64}(g.X); Yf = Float64.(g.Y)
     out = Vector{Float64}(undef, R * samplesPerPosterior)
-    dts = Float64[doT]
-    GC.@preserve packed ret Tf Xf Yf out dts begin
+    dts = Float64[doT]; info = zeros(Cint, R)
+    GC.@preserve packed ret Tf Xf Yf out dts info begin
         check(ccall((:gpslc_sate, LIB[]), Cint,
                     (Ptr{Cvoid}, Cint, Ref{GpslcData}, Ptr{Cdouble}, Cint, Cint, Cint, Ptr{Cint}, Cint, Ptr{Cdouble}, Cint, Cdouble,
                      Cint, UInt64, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cint}),
                     CTX[], 0, data_struct(g, Tf, Xf, Yf), packed, size(packed, 3), 1, size(packed, 1), ret, R, dts, 1,
-                    g.hyperparams.predictionCovarianceNoise, samplesPerPosterior, seed, 0, var_as_std, C_NULL, C_NULL, out, C_NULL))
+                    g.hyperparams.predictionCovarianceNoise, samplesPerPosterior, seed, 0, var_as_std, C_NULL, C_NULL, out, info))
     end
+    check_info(info)
     out
 end
 
@@ -178,19 +212,21 @@ end
     predictCounterfactualEffects(g, nSamplesPerMixture; fidelity=100, minDoT, maxDoT) — replaces src/prediction.jl:23-36:
 one gpslc_ite call for all doT values instead of one sampleITE per doT.
 """
-function predictCounterfactualEffects(g, nSamplesPerMixture::Int; fidelity::Int=100, minDoT=min(g.T...), maxDoT=max(g.T...), seed=UInt64(0))
+function predictCounterfactualEffects(g, nSamplesPerMixture::Int; fidelity::Int=100, minDoT=min(g.T...), maxDoT=max(g.T...), seed=rand(UInt64))
     doTrange = minDoT:(abs(maxDoT - minDoT) / fidelity):maxDoT
     dts = collect(Float64, doTrange); D = length(dts)
     packed = pack(g); ret = retained(g.hyperparams); R = length(ret); n = length(g.Y)
     Tf = Float64.(g.T); Xf = g.X === nothing ? Float64[] : Matrix{Float64}(g.X); Yf = Float64.(g.Y)
     out = Array{Float64}(undef, n, R * nSamplesPerMixture, D)      # C layout [D][1][R*spp][n]
-    GC.@preserve packed ret Tf Xf Yf out dts begin
+    info = zeros(Cint, R * D)
+    GC.@preserve packed ret Tf Xf Yf out dts info begin
         check(ccall((:gpslc_ite, LIB[]), Cint,
                     (Ptr{Cvoid}, Cint, Ref{GpslcData}, Ptr{Cdouble}, Cint, Cint, Cint, Ptr{Cint}, Cint, Ptr{Cdouble}, Cint, Cdouble,
                      Cint, UInt64, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cint}),
                     CTX[], 0, data_struct(g, Tf, Xf, Yf), packed, size(packed, 3), 1, size(packed, 1), ret, R, dts, D,
-                    g.hyperparams.predictionCovarianceNoise, nSamplesPerMixture, seed, 0, C_NULL, C_NULL, out, C_NULL))
+                    g.hyperparams.predictionCovarianceNoise, nSamplesPerMixture, seed, 0, C_NULL, C_NULL, out, info))
     end
+    check_info(info)
     permutedims(out, (3, 1, 2)), doTrange                           # ite[d, n, R*spp] as the reference returns
 end
 
@@ -201,7 +237,7 @@ are the independent units of the sweep; the draws are keyed by the global doT in
 exactly the unsharded result. Returns (ite[d_local, n, R*spp], the full doT range, offset of this block).
 """
 function predictCounterfactualEffectsShard(g, nSamplesPerMixture::Int, world_size::Int, rank::Int; fidelity::Int=100,
-                                           minDoT=min(g.T...), maxDoT=max(g.T...), seed=UInt64(0))
+                                           minDoT=min(g.T...), maxDoT=max(g.T...), seed=UInt64(0))   # all ranks must pass the SAME seed
     doTrange = minDoT:(abs(maxDoT - minDoT) / fidelity):maxDoT
     all = collect(Float64, doTrange); D = length(all)
     base, rem = divrem(D, world_size)
@@ -210,13 +246,15 @@ function predictCounterfactualEffectsShard(g, nSamplesPerMixture::Int, world_siz
     packed = pack(g); ret = retained(g.hyperparams); R = length(ret); n = length(g.Y)
     Tf = Float64.(g.T); Xf = g.X === nothing ? Float64[] : Matrix{Float64}(g.X); Yf = Float64.(g.Y)
     out = Array{Float64}(undef, n, R * nSamplesPerMixture, cnt)
-    GC.@preserve packed ret Tf Xf Yf out dts begin
+    info = zeros(Cint, R * cnt)
+    GC.@preserve packed ret Tf Xf Yf out dts info begin
         check(ccall((:gpslc_ite_slice, LIB[]), Cint,
                     (Ptr{Cvoid}, Cint, Ref{GpslcData}, Ptr{Cdouble}, Cint, Cint, Cint, Ptr{Cint}, Cint, Ptr{Cdouble}, Cint, Cint, Cdouble,
                      Cint, UInt64, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cint}),
                     CTX[], 0, data_struct(g, Tf, Xf, Yf), packed, size(packed, 3), 1, size(packed, 1), ret, R, dts, cnt, off,
-                    g.hyperparams.predictionCovarianceNoise, nSamplesPerMixture, seed, 0, C_NULL, C_NULL, out, C_NULL))
+                    g.hyperparams.predictionCovarianceNoise, nSamplesPerMixture, seed, 0, C_NULL, C_NULL, out, info))
     end
+    check_info(info)
     permutedims(out, (3, 1, 2)), doTrange, off
 end
 
@@ -245,6 +283,21 @@ function covBuild(X1::Matrix{Float64}, X2::Matrix{Float64}, LS::Vector{Float64},
                     CTX[], 0, n, 1, D, X1, X2, 1, LS, sc, noise === nothing ? C_NULL : pointer(nz), K))
     end
     K
+end
+
+# ---- persistence: the language-neutral `.gpslc` container of gpslc_b200/io.py (the reference's src/io.jl serialises the Julia
+# object, which only Julia can read). Layout: 8-byte magic "GPSLCB2\0", little-endian UInt64 header length, JSON header
+# {"version","hyperparams","priorparams","seed","arrays":[{"name","dtype","shape"}...]}, then the arrays raw, C order, each padded
+# to 8 bytes. Only the packed posterior samples are needed to rebuild g.posteriorSamples (to_choicemap).
+"write the packed samples [stride, n_chains, nOuter] of a run next to the data, readable by loadGPSLCObject of the Python mirror"
+function savePacked(filename::String, packed::Array{Float64,3}, header_json::String, arrays::Vector{Pair{String,Array}})
+    if length(filename) > 6 && filename[end-5:end] == ".gpslc"; filename = filename[1:end-6]; end       # src/io.jl:15-17
+    open(filename * ".gpslc", "w") do io
+        write(io, b"GPSLCB2\0"); write(io, htol(UInt64(sizeof(header_json)))); write(io, header_json)
+        for (_, a) in vcat(["packed" => packed], arrays)
+            write(io, a); write(io, zeros(UInt8, mod(-sizeof(a), 8)))
+        end
+    end
 end
 
 end # module

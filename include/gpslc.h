@@ -86,7 +86,8 @@ int gpslc_rbf_logpdf(gpslc_ctx* ctx, int loc, int n, int batch, int D, const dou
 
 /* Observed data + confounder structure: the fields SigmaU, obj, X, T, Y of GPSLCObject (src/types.jl:249-258).
  * SigmaU is passed as the object counts generateSigmaU (src/utils.jl:17-33) was built from, plus its eps/cov
- * (priorparams["sigmaUNoise"], ["sigmaUCov"]); the library uses the closed form of that block matrix. */
+ * (priorparams["sigmaUNoise"], ["sigmaUCov"]); the library uses the closed form of that block matrix. Any other SigmaU
+ * goes in densely through sigma_u_dense. */
 typedef struct {
     int n;                 /* individuals */
     int nX;                /* covariates; 0 == `X === nothing` */
@@ -101,6 +102,10 @@ typedef struct {
     double sigma_u_cov;    /* 1.0 by default  (src/hyperparameters.jl:67) */
     int per_chain_data;    /* 0: X, T, Y are one dataset shared by all chains (the reference's case); 1: X, T, Y hold n_chains
                               datasets back to back (chain-major) — simulation-based calibration runs, test/sbc.jl shape */
+    const double* sigma_u_dense; /* NULL, or (with n_obj == 0) an arbitrary symmetric positive definite SigmaU, n x n column-major:
+                              samplePosterior(hyperparams, priorparams, SigmaU, X, T, Y) accepts any matrix (src/driver.jl:59-69)
+                              and generateU factors uNoise*SigmaU on every update (src/model_prior.jl:27-30). The library factors
+                              SigmaU once (GPSLC_ERR_NOT_PD if that fails) and uses L_S for the U prior density and draws. */
 } gpslc_data;
 
 /* InvGamma(shape, scale) priors of src/hyperparameters.jl:39-65 in the order
@@ -117,7 +122,14 @@ typedef struct {
     uint64_t seed;                  /* Philox key */
     int chain_offset;               /* global id of chain 0 (multi-GPU sharding keeps streams independent of the split) */
     int u_layout_mode;              /* 0: reference toMatrix interleave (identity when nU == 1); 1: column-wise */
-    int ess_rule;                   /* 0: Gen's joint-weight elliptical_slice test; 1: likelihood only */
+    int ess_rule;                   /* acceptance test of every elliptical_slice update (U_k and, for binary T, logitT):
+                                       0: Gen's `while weight <= log(u)` with the FULL `update` weight, i.e. including the Gaussian
+                                          prior density of the sliced address (Gen 0.4 inference/elliptical_slice.jl as recollected,
+                                          SURVEY.md App. C). Default, because the target is the reference's behaviour. CAVEAT: this
+                                          rule counts the prior twice, so the chain does NOT target the model's posterior:
+                                          simulation-based calibration fails for uNoise and the U-dependent statistics
+                                          (p ~ 0, profiles/sbc_r01.md; asserted in tests/test_gpu_sbc.py).
+                                       1: textbook elliptical slice sampling (likelihood terms only): calibrated. */
     int observe_x;                  /* no-U models: 0 = reference behaviour (X never observed, App. B3), 1 = condition on X */
 } gpslc_opts;
 

@@ -36,18 +36,19 @@ def prepare_data(path_or_df, eps=1.0e-13, cov=1.0):
     return counts, obj, X, T, Y
 
 
-def model_data_from_arrays(counts, X, T, Y, nU=1, prior=None, u_layout_reference=True):
+def model_data_from_arrays(counts, X, T, Y, nU=1, prior=None, u_layout_reference=True, sigma_u_dense=None):
     """Assemble ModelData the way the GPSLCObject constructors dispatch (src/types.jl:271-290): no SigmaU => nU=0."""
     T = np.asarray(T)
     binary = T.dtype == np.bool_
     n = T.shape[0]
     prior = dict(prior) if prior is not None else get_prior_parameters()
-    spec = ModelSpec(n=n, nU=(nU if counts is not None else 0), nX=(0 if X is None else X.shape[1]), binary=binary,
+    spec = ModelSpec(n=n, nU=(nU if (counts is not None or sigma_u_dense is not None) else 0), nX=(0 if X is None else X.shape[1]), binary=binary,
                      u_layout_reference=u_layout_reference)
     return ModelData(spec=spec, X=None if X is None else np.asarray(X, dtype=np.float64),
                      T=T.astype(np.float64), Y=np.asarray(Y, dtype=np.float64),
                      counts=list(counts) if counts is not None else [],
-                     eps=prior["sigmaUNoise"], cov=prior["sigmaUCov"], prior=prior)
+                     eps=prior["sigmaUNoise"], cov=prior["sigmaUCov"], prior=prior,
+                     sigma_u_dense=None if sigma_u_dense is None else np.asarray(sigma_u_dense, dtype=np.float64))
 
 
 def synthetic(n, n_obj, nX, seed=1234):

@@ -15,7 +15,7 @@ import scipy.linalg as sla
 
 from . import philox as px
 from .kernel import rbf_kernel_log, process_cov
-from .model import (ModelSpec, ModelData, State, ig_logpdf, u_prior_logpdf, u_prior_quad_logdet, factor_logpdf,
+from .model import (ModelSpec, ModelData, State, ig_logpdf, u_prior_logpdf, u_prior_logpdf_data, u_prior_quad_logdet, factor_logpdf,
                     factor_cov, factor_exists, bernoulli_logpmf, log_joint, effective_uxls, LOG_2PI)
 
 
@@ -72,7 +72,7 @@ class Scorer:
         d = self.data
         if self.mode == "faithful":
             self.n_chol += 1  # the reference factorises uNoise*SigmaU on every update (model_prior.jl:27-30)
-        return u_prior_logpdf(st.U[i], st.theta[d.spec.idx("uNoise")], d.counts, d.eps, d.cov)
+        return u_prior_logpdf_data(d, st.U[i], st.theta[d.spec.idx("uNoise")])
 
     def rescore(self, st_new, factors, u_terms):
         """Return (delta_loglik_terms, new_cache) for a proposed state. In faithful mode everything is recomputed
@@ -106,6 +106,13 @@ def sample_u_prior(stream, n, counts, u_noise, eps, cov):
     return math.sqrt(u_noise) * (math.sqrt(cov) * zo[obj] + math.sqrt(d) * zi)
 
 
+def sample_u_prior_data(data, stream, u_noise):
+    """U ~ N(0, uNoise*SigmaU): block form, or sqrt(uNoise) * L_S z for a dense SigmaU (z = the stream's first n normals)."""
+    if data.sigma_u_dense is None:
+        return sample_u_prior(stream, data.spec.n, data.counts, u_noise, data.eps, data.cov)
+    return math.sqrt(u_noise) * (data.sigma_u_chol() @ stream.normal_vector(data.spec.n))
+
+
 def generate_initial_state(data, seed, chain, observe_x=False):
     """Gen `generate(model, args, obs)` (src/inference.jl:20,73,123,156,189,261,321,370): unobserved addresses are
     drawn from their priors in model order."""
@@ -120,7 +127,7 @@ def generate_initial_state(data, seed, chain, observe_x=False):
     U = np.zeros((spec.nU, spec.n))
     for k in range(spec.nU):
         s = px.Stream(seed, chain, k, px.stream_b(px.TAG_INIT_VEC, 0))
-        U[k] = sample_u_prior(s, spec.n, data.counts, theta[spec.idx("uNoise")], data.eps, data.cov)
+        U[k] = sample_u_prior_data(data, s, theta[spec.idx("uNoise")])
     st = State(theta, U)
     if (not spec.has_u) and spec.has_x and not observe_x:
         st.Xmodel = np.zeros((spec.n, spec.nX))
@@ -179,8 +186,7 @@ def mh_site(data, st, sc, site_index, name, i, j, seed, chain, it):
 def ess_u(data, st, sc, k, seed, chain, it, stats=None, ess_rule="gen_joint_weight"):
     """`elliptical_slice(trace, :U=>k=>:U, zeros(n), uCov)` (src/inference.jl:50-54)."""
     spec = data.spec
-    nu = sample_u_prior(px.Stream(seed, chain, k, px.stream_b(px.TAG_ESS_NU, it)), spec.n, data.counts,
-                        st.theta[spec.idx("uNoise")], data.eps, data.cov)
+    nu = sample_u_prior_data(data, px.Stream(seed, chain, k, px.stream_b(px.TAG_ESS_NU, it)), st.theta[spec.idx("uNoise")])
     sca = px.Stream(seed, chain, k, px.stream_b(px.TAG_ESS_SCALAR, it))
     u, v = sca.uniform_pair()
     logu = math.log(u)
@@ -227,7 +233,7 @@ def logit_t_cov(data, st):
     return process_cov(logk, th[spec.idx("tScale")], th[spec.idx("tNoise")])
 
 
-def ess_logit_t(data, st, sc, L_stale, seed, chain, it, stats=None):
+def ess_logit_t(data, st, sc, L_stale, seed, chain, it, stats=None, ess_rule="gen_joint_weight"):
     """`elliptical_slice(trace, :logitT, zeros(n), logitTCov)` (src/inference.jl:233, 293, 347); the prior draw ν uses
     the covariance computed once per outer iteration (App. B6) while the weight uses the model's current one."""
     spec = data.spec
@@ -247,6 +253,8 @@ def ess_logit_t(data, st, sc, L_stale, seed, chain, it, stats=None):
         st_new = st.copy()
         st_new.logitT = f * math.cos(theta) + nu * math.sin(theta)
         w, cache = sc.rescore(st_new, [fT], [])
+        if ess_rule == "likelihood_only":
+            w = 0.0     # textbook rule: only the Bernoulli likelihood of the sliced address enters the test
         w += bernoulli_logpmf(data.T, st_new.logitT) - bern_old
         evals += 1
         if not (w <= logu) or evals >= ESS_MAX_EVALS:
@@ -306,7 +314,7 @@ def posterior(data, nOuter, nMHInner, nESInner, seed=0, chain=0, mode="increment
             for j in range(nESInner if (spec.has_u or spec.has_x) else 0):
                 it = i * nESInner + j
                 if do_logit:
-                    ess_logit_t(data, st, sc, L_stale, seed, chain, it, stats)
+                    ess_logit_t(data, st, sc, L_stale, seed, chain, it, stats, ess_rule)
                 for k in range(spec.nU):
                     ess_u(data, st, sc, k, seed, chain, it, stats, ess_rule)
         out[i] = pack_sample(spec, st)

@@ -208,6 +208,17 @@ def u_prior_logpdf(u, u_noise, counts, eps, cov):
     return -0.5 * (n * LOG_2PI + n * math.log(u_noise) + logdet + quad / u_noise)
 
 
+def u_prior_logpdf_data(data, u, u_noise):
+    """log N(u; 0, uNoise * SigmaU) for the SigmaU of `data`: closed form for the block matrix, Cholesky for a dense one
+    (L_S^-1 u with L_S = chol(SigmaU); chol(uNoise*SigmaU) = sqrt(uNoise) L_S)."""
+    if data.sigma_u_dense is None:
+        return u_prior_logpdf(u, u_noise, data.counts, data.eps, data.cov)
+    L = data.sigma_u_chol()
+    z = sla.solve_triangular(L, u, lower=True, check_finite=False)
+    n = u.shape[0]
+    return -0.5 * (n * LOG_2PI + n * math.log(u_noise) + 2.0 * float(np.sum(np.log(np.diag(L)))) + float(z @ z) / u_noise)
+
+
 def bernoulli_logpmf(t, logit_t):
     """Σ_i log Bernoulli(T_i; expit(logitT_i)) (src/model_prior.jl:22-24), in the overflow-safe form."""
     x = np.asarray(logit_t, dtype=np.float64)
@@ -231,6 +242,13 @@ class ModelData:
     eps: float = 1e-13
     cov: float = 1.0
     prior: dict = field(default_factory=get_prior_parameters)
+    sigma_u_dense: np.ndarray = None  # an unstructured SigmaU (src/driver.jl:59-69 accepts any matrix): Cholesky path
+
+    def sigma_u_chol(self):
+        """lower Cholesky factor of the dense SigmaU (what generateU's mvnormal computes, src/model_prior.jl:27-30)"""
+        if getattr(self, "_ls", None) is None:
+            self._ls = sla.cholesky(self.sigma_u_dense, lower=True, check_finite=False)
+        return self._ls
 
 
 @dataclass
@@ -346,7 +364,7 @@ def log_joint_terms(data, st):
         terms[(name, i, j)] = ig_logpdf(st.theta[spec.idx(name, i, j)], pr[a], pr[b])
     if spec.has_u:
         for i in range(spec.nU):
-            terms[("U", i)] = u_prior_logpdf(st.U[i], st.theta[spec.idx("uNoise")], data.counts, data.eps, data.cov)
+            terms[("U", i)] = u_prior_logpdf_data(data, st.U[i], st.theta[spec.idx("uNoise")])
     for f in range(spec.nX + 2):
         terms[("factor", f)] = factor_logpdf(data, st, f)
     if spec.binary:

@@ -103,19 +103,26 @@ class Stream:
         return math.sqrt(-2.0 * math.log(u1)) * math.cos(2.0 * math.pi * u2)
 
     def gamma(self, shape):
-        """Marsaglia-Tsang (2000) for shape >= 1; one normal block + one uniform block per attempt."""
-        assert shape >= 1.0
-        d = shape - 1.0 / 3.0
+        """Marsaglia-Tsang (2000); one normal block + one uniform block per attempt; shape < 1 through the boost
+        Gamma(a) = Gamma(a+1) * U^(1/a). Same bounded loop as csrc/rng.cuh."""
+        assert shape > 0.0
+        a = shape + 1.0 if shape < 1.0 else shape
+        d = a - 1.0 / 3.0
         c = 1.0 / math.sqrt(9.0 * d)
-        while True:
+        g = d
+        for _ in range(256):
             x = self.normal()
             u = self.uniform()
             v = 1.0 + c * x
             if v <= 0.0:
                 continue
             v = v * v * v
+            g = d * v
             if math.log(u) < 0.5 * x * x + d - d * v + d * math.log(v):
-                return d * v
+                break
+        if shape < 1.0:
+            g *= self.uniform() ** (1.0 / shape)
+        return g
 
     def inv_gamma(self, shape, scale):
         """Gen `inv_gamma(shape, scale)` == scale / Gamma(shape, 1)."""

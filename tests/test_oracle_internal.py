@@ -156,3 +156,23 @@ def test_prepare_data_sorts_by_obj(tmp_path):
     assert counts == [2, 2] and list(obj) == ["a", "a", "b", "b"] and list(T) == [0.2, 0.4, 0.1, 0.3]   # src/data.jl:25
     counts, obj, X, T, Y = od.prepare_data(df.drop(columns=["obj", "X1"]))
     assert counts is None and obj is None and X is None
+
+
+def test_gamma_sampler_small_shapes_and_dense_sigma_u():
+    """The Philox gamma sampler (shared specification with csrc/rng.cuh) covers shape < 1 through the boost
+    Gamma(a) = Gamma(a+1) U^(1/a); a dense SigmaU scores and samples like the closed form of the block matrix."""
+    import scipy.stats as sst
+    from oracle import philox as px, model as om, inference as oi, data as od
+    for shape in (0.3, 0.9, 1.0, 4.0):
+        x = np.array([px.Stream(5, c, 1, 2).gamma(shape) for c in range(4000)])
+        assert sst.kstest(x, sst.gamma(shape).cdf).pvalue > 1e-3, shape
+    counts, X, T, Y = od.synthetic(24, 3, 2, seed=3)
+    S = om.generate_sigma_u(counts, 0.25, 0.5)             # well conditioned, so the Cholesky route is accurate
+    pri = {**om.get_prior_parameters(), "sigmaUNoise": 0.25, "sigmaUCov": 0.5}
+    blk = od.model_data_from_arrays(counts, X, T, Y, nU=1, prior=pri)
+    dns = od.model_data_from_arrays(None, X, T, Y, nU=1, prior=pri, sigma_u_dense=S)
+    u = np.random.default_rng(0).standard_normal(24)
+    assert abs(om.u_prior_logpdf_data(blk, u, 1.3) - om.u_prior_logpdf_data(dns, u, 1.3)) < 1e-10
+    assert dns.spec.nU == 1
+    a, _ = oi.posterior(dns, 2, 1, 1, seed=3, chain=0)
+    assert a.shape == (2, dns.spec.n_params + 24) and np.all(np.isfinite(a[:, dns.spec.n_params:]))
