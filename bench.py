@@ -8,6 +8,14 @@ One "step" = one Metropolis-Hastings sweep (the body of `for j = 1:nMHInner`, /r
 S = 6 + nU(2+nX) + 4nX = 58 single-site updates) of EVERY chain on the rank: config c3 of BASELINE.json — synthetic
 n=1024, 16 confounder objects, 10-dim X, 512 chains per GPU (weak scaling: chains are independent, no data-path
 collective). Prints ONE JSON line (rank 0).
+
+Keys beyond the contract:
+  e2e      the reference's call sequence through the host-buffer API: Posterior(...) with the DEFAULT inner budget
+           (nMHInner=10, nESInner=5; only nOuter is shortened) followed by sampleSATE(doT=0, samplesPerPosterior=10) for every
+           chain; at N > 1 the packed samples are gathered over NCCL (device buffers) inside the timed region.
+  c2, c4   the other single-GPU BASELINE configurations (sweeps/s and fraction of the FP64 peak); c5 when N == 8.
+  strong   (N > 1) the same kernel with 512 chains TOTAL, i.e. 512/N per GPU.
+  cpu_baseline.variants  the oracle port in the reference's cost model (all cores / one BLAS thread) and incrementally.
 """
 import argparse
 import json
@@ -25,7 +33,8 @@ import numpy as np  # noqa: E402
 
 WORKLOAD = dict(name="c3", n=1024, n_obj=16, nX=10, nU=1, chains_per_gpu=512)
 FP64_PEAK_FILE = os.path.join(ROOT, "profiles", "fp64_peak_r01.json")
-TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")   # dram bytes per mh_lanes launch from `ncu --set full`
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")   # dram bytes per mh_lanes launch from `ncu --set full`
+TRAFFIC_FILE_OLD = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
 
 
 def synthetic(n, n_obj, nX, seed=1234):
@@ -102,22 +111,26 @@ def fp64_peak():
 
 
 def ncu_traffic():
-    try:
-        return float(json.load(open(TRAFFIC_FILE))["dram_bytes_per_launch"])
-    except Exception:
-        return None
+    for f in (TRAFFIC_FILE, TRAFFIC_FILE_OLD):
+        try:
+            return float(json.load(open(f))["dram_bytes_per_launch"])
+        except Exception:
+            continue
+    return None
 
 
-def cpu_sample(steps_sites=6, threads=None):
-    """Bounded sample of the SAME workload on the host cores: the first `steps_sites` single-site MH updates of one
-    sweep of one chain, with the reference's cost model (every update re-scores the whole model: nX+5 kernel builds and
-    nU+nX+2 Choleskys) executed by the NumPy/SciPy oracle port."""
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
+def cpu_sample(mode="faithful"):
+    """Bounded sample of the SAME workload on the host cores: single-site MH updates of one sweep of one chain executed by the
+    NumPy/SciPy oracle port. mode "faithful" = the reference's cost model (every update re-scores the whole model: nX+5 kernel
+    builds and nU+nX+2 Choleskys, the U-prior one included — SURVEY.md §3.2); "incremental" = one build + one Cholesky per update
+    (the algorithm the CUDA path runs)."""
     from oracle import data as od, inference as oi
     w = WORKLOAD
     counts, X, T, Y = od.synthetic(w["n"], w["n_obj"], w["nX"])
     md = od.model_data_from_arrays(counts, X, T, Y, nU=w["nU"])
     st = oi.generate_initial_state(md, 1234, 0)
-    sc = oi.Scorer(md, st, "faithful")
+    sc = oi.Scorer(md, st, mode)
     sites = md.spec.mh_sites()
 
     def run(first, count):
@@ -129,11 +142,35 @@ def cpu_sample(steps_sites=6, threads=None):
     return run, len(sites)
 
 
+def cpu_variants(budget_s=22.0):
+    """The three CPU figures BASELINE.md §4.3 asks for, each a bounded sample scaled to sweeps/s of one chain."""
+    from threadpoolctl import threadpool_limits
+    cores = os.cpu_count()
+    out = {}
+    plan = [("faithful_all_cores", "faithful", None, 24), ("incremental_all_cores", "incremental", None, 58),
+            ("faithful_1_thread", "faithful", 1, 5), ("incremental_1_thread", "incremental", 1, 20)]
+    for key, mode, thr, nsite in plan:
+        run, S = cpu_sample(mode)
+        if thr is None:
+            run(0, 2)
+            t = run(2, nsite)
+        else:
+            with threadpool_limits(limits=thr):
+                run(0, 1)
+                t = run(1, nsite)
+        out[key] = {"value": (nsite / S) / t, "unit": "sweeps/s (one chain)", "blas_threads": cores if thr is None else thr,
+                    "sites_timed": nsite, "seconds": t}
+    out["note"] = ("faithful = the reference's cost (full model re-score per single-site update: 15 kernel builds + 13 Choleskys incl. the "
+                   "U prior); incremental = 1 build + 1 Cholesky per update (what the CUDA path computes). The reference is one chain on "
+                   f"one thread: 1-thread x {cores} cores = an ideal many-chain projection of {cores} independent chains")
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    run, S = cpu_sample()
+    run, S = cpu_sample("faithful")
     sites_per_step = 6
     pos = 0
     for _ in range(args.warmup):
@@ -156,27 +193,30 @@ def run_reference(args):
     emit(line)
 
 
+# ------------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
     import torch
     import gpslc_b200 as g
-    from gpslc_b200.inference import ChainSampler, Posterior
+    from gpslc_b200 import estimation as ge
+    from gpslc_b200.inference import ChainSampler
+    from gpslc_b200.parallel import all_gather_samples_device
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=dev)
     w = WORKLOAD
     C = w["chains_per_gpu"]
     counts, X, T, Y = synthetic(w["n"], w["n_obj"], w["nX"])
     pri = default_priors()
     ctx = g.Context(local)
-    smp = ChainSampler(pri, X, T, Y, w["nU"], counts, nOuter=24, nMHInner=10, nESInner=5, n_chains=C, seed=1234,
-                       chain_offset=rank * C, ctx=ctx)
-    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
-    S = smp.n_sites
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    peak, peak_src = fp64_peak()
 
     def barrier():
         ctx.synchronize()
@@ -184,6 +224,31 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
 
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        tt = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    def time_sweeps(smp, steps, warmup):
+        """`steps` single-sweep launches timed with CUDA events on the library's stream; returns (total ms max over ranks,
+        per-launch ms list of this rank)."""
+        for _ in range(warmup):
+            smp.mh_sweeps(1)
+        barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        ev[0].record(stream)
+        for k in range(steps):
+            smp.mh_sweeps(1)
+            ev[k + 1].record(stream)
+        barrier()
+        return max_over_ranks(ev[0].elapsed_time(ev[-1])), [ev[k].elapsed_time(ev[k + 1]) for k in range(steps)]
+
+    # ---- headline: c3, one MH sweep of every chain per step
+    smp = ChainSampler(pri, X, T, Y, w["nU"], counts, nOuter=24, nMHInner=10, nESInner=5, n_chains=C, seed=1234,
+                       chain_offset=rank * C, ctx=ctx)
+    S = smp.n_sites
     for _ in range(args.warmup):
         smp.mh_sweeps(1)
     barrier()
@@ -191,64 +256,92 @@ def run_ours(args):
     if rank == 0:
         clocks.start()
         time.sleep(0.3)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     launches0 = ctx.launches
-    barrier()
     t0 = time.time()
-    ev[0].record(stream)
-    for k in range(args.steps):
-        smp.mh_sweeps(1)
-        ev[k + 1].record(stream)
-    barrier()
+    ms, per_launch_ms = time_sweeps(smp, args.steps, 0)
     t1 = time.time()
     launches = ctx.launches - launches0
-    ms = ev[0].elapsed_time(ev[-1])
-    per_launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     clk = clocks.stop(t0, t1) if rank == 0 else None
     acc, _ = smp.stats()
-    if world > 1:
-        tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
     value = world * C * args.steps / (ms * 1e-3)
+    state_c3 = smp.state() if not args.no_e2e else None
+    smp.close()
 
-    # ---- e2e: the public API call with HOST buffers (Posterior == gpslc_posterior): data H2D, `generate`, 10 MH sweeps
-    # (default nMHInner) of every chain, packed samples D2H — all inside the timed region.
-    e2e_sweeps = 10
-    def e2e_call(seed):
-        return Posterior({**pri, "_obj_counts": counts}, X, T, Y, w["nU"], 1, e2e_sweeps, 0, n_chains=C, seed=seed,
-                         chain_offset=rank * C, ctx=ctx)
-    e2e_reps = 0 if args.no_e2e else 2
-    out = e2e_call(1) if not args.no_e2e else np.zeros(1)
-    barrier()
-    te = time.perf_counter()
-    for r in range(e2e_reps):
-        tc = time.perf_counter()
-        out = e2e_call(2 + r)
-        if rank == 0:
-            print(f"e2e call {r}: {time.perf_counter() - tc:.3f} s", file=sys.stderr)
-    barrier()
-    te = time.perf_counter() - te
-    if world > 1:
-        tt = torch.tensor([te], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        te = float(tt.item())
-    e2e_value = world * C * e2e_sweeps * e2e_reps / te if e2e_reps else None
-    h2d = (X.size + T.size + Y.size) * 8 + 4 * len(counts) + 27 * 8
-    d2h = out.size * 8
+    def frac_of(n, nX, chains, sec_per_sweep, S_):
+        return chains * (S_ - 1) * (n ** 3 / 3.0 + 2.0 * n * n) / sec_per_sweep / 1e12
+
+    # ---- strong-scaling point: the same 512 chains spread over the N GPUs (64 per GPU at N = 8)
+    strong = None
+    if world > 1 and not args.no_extra:
+        Cs = C // world
+        s2 = ChainSampler(pri, X, T, Y, w["nU"], counts, 24, 10, 5, n_chains=Cs, seed=1234, chain_offset=rank * Cs, ctx=ctx)
+        ms2, _ = time_sweeps(s2, 5, 2)
+        s2.close()
+        tf = frac_of(w["n"], w["nX"], Cs, ms2 * 1e-3 / 5, S)
+        strong = {"chains_total": Cs * world, "chains_per_gpu": Cs, "value": Cs * world * 5 / (ms2 * 1e-3), "unit": "sweeps/s",
+                  "ms_per_step": ms2 / 5, "tflops_per_gpu": tf, "frac_per_gpu": tf / peak}
+
+    # ---- e2e: the reference's call sequence with HOST buffers: Posterior with the default inner budget
+    # (10 MH sweeps + 5 elliptical-slice passes per outer iteration; nOuter shortened to E_OUTER) + sampleSATE(doT=0, 10 draws per
+    # retained sample) for every chain; at N > 1 the packed samples are all-gathered over NCCL from the device buffers.
+    e2e = None
+    if not args.no_e2e:
+        E_OUTER, nMH, nES, spp = 2, 10, 5, 10
+        ret = np.arange(E_OUTER, dtype=np.int32)
+        pin = lambda shape: torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
+        # untimed warm-up of the same call sequence at the smallest budget (sizes the library's workspaces and staging arena, first use
+        # of the cluster-team kernels of the slice sampler's tail rounds)
+        sw = ChainSampler(pri, X, T, Y, w["nU"], counts, 1, 1, 1, n_chains=C, seed=98, chain_offset=rank * C, ctx=ctx)
+        sw.run(1)
+        pw = sw.samples()
+        sw.close()
+        ge.sate(pw, X, T, Y, w["nU"], 0.0, np.zeros(1, dtype=np.int32), 1e-10, spp, seed=98, chain_offset=rank * C, ctx=ctx)
+        barrier()
+        te = time.perf_counter()
+        s3 = ChainSampler(pri, X, T, Y, w["nU"], counts, E_OUTER, nMH, nES, n_chains=C, seed=99, chain_offset=rank * C, ctx=ctx)   # H2D + generate
+        s3.run(E_OUTER)
+        gather_ms = 0.0
+        gathered_bytes = 0
+        if world > 1:
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ctx.synchronize()
+            g0.record()
+            allsamp = all_gather_samples_device(s3, world)          # [world, nOuter, C, stride] on the device, NCCL over NVLink
+            g1.record()
+            torch.cuda.synchronize()
+            gather_ms = g0.elapsed_time(g1)
+            gathered_bytes = allsamp.numel() * 8
+            if rank == 0:
+                host_all = pin(tuple(allsamp.shape))
+                torch.from_numpy(host_all).copy_(allsamp)            # the gathered posterior lands on rank 0's host
+        packed = s3.samples()                                        # D2H of this rank's [nOuter, C, stride]
+        _, ess_ev = s3.stats()
+        s3.close()
+        so = ge.sate(packed, X, T, Y, w["nU"], 0.0, ret, 1e-10, spp, seed=99, chain_offset=rank * C, ctx=ctx)   # H2D samples, D2H draws
+        barrier()
+        te = max_over_ranks(time.perf_counter() - te)
+        gather_ms = max_over_ranks(gather_ms)
+        h2d = (X.size + T.size + Y.size) * 8 * 2 + 4 * len(counts) + 27 * 8 + packed.size * 8
+        d2h = packed.size * 8 + so["samples"].size * 8 + so["mean"].size * 16 + so["info"].size * 4 + (gathered_bytes if rank == 0 else 0)
+        e2e = {"value": world * C * E_OUTER * nMH / te, "unit": "sweeps/s", "h2d_bytes_per_step": int(h2d / (E_OUTER * nMH)),
+               "d2h_bytes_per_step": int(d2h / (E_OUTER * nMH)), "seconds": te,
+               "outer_iterations_per_s": world * C * E_OUTER / te,
+               "sate_samples": int(so["samples"].size), "sate_all_pd": bool(so["info"].max() == 0),
+               "ess_evals_per_slice_mean": float(ess_ev.mean() / (E_OUTER * nES)),
+               "gather_ms": gather_ms, "gathered_bytes": int(gathered_bytes),
+               "call": f"Posterior(host X,T,Y; nOuter={E_OUTER}, nMHInner={nMH}, nESInner={nES} (the default inner budget), {C} chains per GPU) "
+                       f"+ sampleSATE(doT=0, samplesPerPosterior={spp}) for every chain; incl. generate, H2D, D2H"
+                       + (", NCCL all_gather of the device-resident samples" if world > 1 else "")}
 
     # ---- second half of BASELINE.json's metric: ITE samples/sec. One ITE sample = one length-n draw from N(MeanITE, CovITE)
     # (src/estimation.jl:105). The current state of every chain serves as one retained posterior sample: C tasks, each one
     # augmented 2n x 2n Cholesky + spp draws, through the host-buffer C ABI (H2D of the samples, D2H of the draws included).
     ite = None
     if not args.no_e2e:
-        from gpslc_b200 import estimation as ge
         spp = 10
-        packed = smp.state()[None, :, :]
+        packed = state_c3[None, :, :]
         ret0 = np.zeros(1, dtype=np.int32)
         ite_reps = 2
-        # pinned host buffers for the posterior samples going in and the means / draws coming out, reused across calls as a
-        # serving loop would; the copies in both directions are inside the timed region
         pin = lambda shape: torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
         packed_pin = pin(packed.shape); packed_pin[...] = packed
         obuf = {"mean": pin((1, C, 1, w["n"])), "samples": pin((1, C, spp, w["n"]))}
@@ -258,11 +351,7 @@ def run_ours(args):
         for r in range(ite_reps):
             o = ge.ite(packed_pin, X, T, Y, w["nU"], 0.0, ret0, 1e-10, spp, seed=2 + r, chain_offset=rank * C, ctx=ctx, out=obuf)
         barrier()
-        ti = (time.perf_counter() - ti) / ite_reps
-        if world > 1:
-            tt = torch.tensor([ti], device="cuda", dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ti = float(tt.item())
+        ti = max_over_ranks((time.perf_counter() - ti) / ite_reps)
         nI = w["n"]
         ite = {"value": world * C * spp / ti, "unit": "ITE samples/s", "seconds": ti,
                "workload": f"sampleITE(doT=0) for {C} posterior samples per GPU (one per chain) x {spp} draws at n={nI}: "
@@ -270,12 +359,27 @@ def run_ours(args):
                "h2d_bytes_per_call": int(packed.nbytes + (X.size + T.size + Y.size) * 8), "d2h_bytes_per_call": int(obuf["mean"].nbytes + obuf["samples"].nbytes),
                "tflops": world * C * (8.0 * nI ** 3 / 3.0) / ti / 1e12, "all_pd": bool(o["info"].max() == 0)}
 
+    # ---- the other BASELINE configurations, device-timed like the headline (rank-local, weak scaling)
+    extra = {}
+    if not args.no_extra:
+        for name, n2, nobj2, nX2, C2, st2, wu2 in (("c2", 256, 4, 5, 1024, 5, 3), ("c4", 4096, 64, 10, 64, 2, 1)):
+            c2_, X2, T2, Y2 = synthetic(n2, nobj2, nX2)
+            sx = ChainSampler(pri, X2, T2, Y2, 1, c2_, 24, 10, 5, n_chains=C2, seed=1234, chain_offset=rank * C2, ctx=ctx)
+            msx, _ = time_sweeps(sx, st2, wu2)
+            Sx = sx.n_sites
+            sx.close()
+            tf = frac_of(n2, nX2, C2, msx * 1e-3 / st2, Sx)
+            extra[name] = {"value": world * C2 * st2 / (msx * 1e-3), "unit": "sweeps/s", "ms_per_step": msx / st2, "steps": st2, "warmup": wu2,
+                           "tflops_per_gpu": tf, "frac": tf / peak,
+                           "workload": f"n={n2}, {nobj2} objects, nX={nX2}, nU=1, {C2} chains per GPU, {Sx} sites per sweep"}
+        if world == 8:
+            extra["c5"] = run_c5(g, ge, ctx, rank, world, pri, peak, barrier, max_over_ranks)
+
     if rank == 0:
         n = w["n"]
         flops_per_factor = n ** 3 / 3.0 + 2.0 * n * n
         flops_per_launch = C * (S - 1) * flops_per_factor   # the uNoise site needs no factorisation (App. A4)
         avg_launch_s = float(np.mean(per_launch_ms)) * 1e-3
-        peak, peak_src = fp64_peak()
         achieved = flops_per_launch / avg_launch_s / 1e12
         line = {"metric": "mh_sweeps_per_sec", "value": value, "unit": "sweeps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -285,30 +389,58 @@ def run_ours(args):
                            "chains_per_gpu": C, "sites_per_sweep": S,
                            "l2": "working set (296 resident factor scratch slots x 4.25 MiB = 1.26 GB) exceeds the 126 MB L2; no explicit flush",
                            "seed": 1234},
-                "clocks": clk, "gpu_launches": int(launches),
-                "e2e": {"value": e2e_value, "unit": "sweeps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "call": f"Posterior(host X,T,Y; nOuter=1, nMHInner={e2e_sweeps}, nESInner=0, {C} chains) incl. generate + H2D + D2H"},
+                "clocks": clk, "gpu_launches": int(launches), "e2e": e2e,
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                              "traffic": ncu_traffic(), "kernel": "mh_lanes_kernel (fused RBF build + blocked Cholesky + solve, DMMA)",
                              "algorithmic": f"{S - 1} factors x (n^3/3 + 2n^2) flops x {C} chains per launch",
                              "peak_source": peak_src},
                 "mh_accept_rate": float(acc.sum() / max(1, C * S * (args.warmup + args.steps))), "ite": ite}
-        # ---- CPU baseline on the box's host cores (bounded sample, rank 0 at N=1 only)
+        line.update(extra)
+        if strong is not None:
+            line["strong"] = strong
+        # ---- CPU baseline on the box's host cores (bounded samples, rank 0 at N=1 only)
         if world == 1 and not args.no_cpu:
-            run, Ssites = cpu_sample()
-            run(0, 2)
-            nsite = Ssites                      # one full sweep of one chain (about 10-15 s of CPU work)
-            tc = run(2, nsite)
-            line["cpu_baseline"] = {"value": (nsite / Ssites) / tc, "unit": "sweeps/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"{nsite} of {Ssites} single-site MH updates of one sweep of one chain at the c3 shape, "
-                                              "reference cost model (full model re-score per update), NumPy/SciPy oracle port with "
-                                              f"BLAS threads = all {os.cpu_count()} host cores; {tc:.1f} s of CPU work"}
+            v = cpu_variants()
+            fa = v["faithful_all_cores"]
+            line["cpu_baseline"] = {"value": fa["value"], "unit": "sweeps/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"{fa['sites_timed']} of 58 single-site MH updates of one sweep of one chain at the c3 shape, "
+                                              "reference cost model (full model re-score per update, U-prior Cholesky executed), NumPy/SciPy "
+                                              f"oracle port with BLAS threads = all {os.cpu_count()} host cores; {fa['seconds']:.1f} s of CPU work",
+                                    "variants": v}
         emit(line)
-    smp.close()
     ctx.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_c5(g, ge, ctx, rank, world, pri, peak, barrier, max_over_ranks, n_dot=256, n=8192):
+    """BASELINE c5: predictCounterfactualEffects over 256 doT at n=8192 for ONE posterior sample, 32 doT per GPU. The posterior
+    sample is a sampled one: a single chain (same seed on every rank, hence the same sample) after one outer iteration."""
+    from gpslc_b200.inference import ChainSampler
+    from gpslc_b200.parallel import shard_chains
+    spp = 10
+    counts, X, T, Y = synthetic(n, n // 64, 10)
+    t0 = time.perf_counter()
+    s = ChainSampler(pri, X, T, Y, 1, counts, 1, 1, 1, n_chains=1, seed=5, ctx=ctx)
+    s.run(1)
+    smp = s.samples()
+    s.close()
+    t_fit = time.perf_counter() - t0
+    doT = np.linspace(T.min(), T.max(), n_dot)
+    off, cnt = shard_chains(n_dot, world, rank)
+    ret = np.zeros(1, dtype=np.int32)
+    ge.ite(smp, X, T, Y, 1, doT[off:off + 2], ret, 1e-10, spp, ctx=ctx, dot_offset=off, want_samples=False)   # sizes the workspace
+    barrier()
+    t0 = time.perf_counter()
+    summ, info = ge.ite_summary(smp, X, T, Y, 1, doT[off:off + cnt], ret, 1e-10, spp, seed=5, ctx=ctx, dot_offset=off)   # draws stay in HBM
+    barrier()
+    t = max_over_ranks(time.perf_counter() - t0)
+    fl = n_dot * (7.0 * n ** 3 / 3.0) + world * n ** 3 / 3.0
+    return {"seconds": t, "tflops_aggregate": fl / t / 1e12, "frac_per_gpu": fl / t / 1e12 / world / peak, "n": n, "n_doT": n_dot,
+            "doT_per_gpu": cnt, "spp": spp, "all_pd": bool(info.max() == 0), "posterior_sample_seconds": t_fit,
+            "flops": f"{n_dot} x 7 n^3/3 (TRSM + SYRK + CovITE factor per doT) + n^3/3 (Kp) once per GPU",
+            "summary_finite": bool(np.isfinite(summ).all())}
 
 
 _JSON_FD = None
@@ -338,7 +470,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-e2e", action="store_true", help="development: skip the e2e leg")
+    ap.add_argument("--no-e2e", action="store_true", help="development: skip the e2e and ITE legs")
+    ap.add_argument("--no-extra", action="store_true", help="development: skip the c2 / c4 / c5 / strong-scaling legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

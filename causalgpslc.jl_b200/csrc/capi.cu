@@ -9,13 +9,14 @@ int launch_chol_logpdf_dense(Ctx*, int, int, const double*, int, const double*, 
 int launch_rbf_logpdf(Ctx*, int, int, int, const double*, size_t, const double*, const double*, const double*, const double*, int,
                       double*, double*, double*, int*);
 
-__global__ void inv_sq_kernel(const double* ls, double* w, size_t n) {
+__global__ void inv_sq_kernel(const double* ls, double* w, size_t n, int square) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i < n) w[i] = 1.0 / (ls[i] * ls[i]);
+    if (i < n) w[i] = square ? 1.0 / (ls[i] * ls[i]) : 1.0 / ls[i];
 }
-int launch_inv_sq(Ctx* ctx, const double* ls, double* w, size_t n) {
+// w = 1 / ls^2 (square = 1) or 1 / ls (square = 0: the pre-scaling factor of the covariance-build kernels)
+int launch_inv_sq(Ctx* ctx, const double* ls, double* w, size_t n, int square) {
     if (n == 0) return GPSLC_OK;
-    inv_sq_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ls, w, n);
+    inv_sq_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ls, w, n, square);
     ctx->launches++;
     GP_CUDA(ctx, cudaGetLastError());
     return GPSLC_OK;
@@ -115,7 +116,7 @@ int gpslc_cov_build(gpslc_ctx* h, int loc, int n, int batch, int D, const double
     GP_TRY(dw.outbuf(1, nullptr, 0));
     double* w = nullptr;
     if (D > 0) { GP_CUDA(ctx, ctx->arena_alloc(reinterpret_cast<void**>(&w), (size_t)batch * D * sizeof(double))); }
-    int rc = launch_inv_sq(ctx, dls.d, w, (size_t)batch * D);
+    int rc = launch_inv_sq(ctx, dls.d, w, (size_t)batch * D, 0);
     if (!rc) rc = launch_cov_build(ctx, n, batch, D, df1.d, df2.d, feat_shared ? 0 : (size_t)D * n, w, dsc.d, noise ? dnz.d : nullptr, dK.d);
     if (!rc) rc = dK.finish();
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
@@ -169,7 +170,7 @@ int gpslc_rbf_logpdf(gpslc_ctx* h, int loc, int n, int batch, int D, const doubl
     GP_TRY(dinfo.outbuf(loc, info, batch));
     double* w = nullptr;
     if (D > 0) GP_CUDA(ctx, ctx->arena_alloc(reinterpret_cast<void**>(&w), (size_t)batch * D * sizeof(double)));
-    int rc = launch_inv_sq(ctx, dls.d, w, (size_t)batch * D);
+    int rc = launch_inv_sq(ctx, dls.d, w, (size_t)batch * D, 1);
     if (!rc) rc = launch_rbf_logpdf(ctx, batch, n, D, df.d, feat_shared ? 0 : (size_t)D * n, w, dsc.d, dnz.d, dy.d, y_shared,
                                     dlp.d, dld.d, dq.d, dinfo.d);
     if (!rc) rc = dlp.finish();
@@ -322,7 +323,8 @@ int launch_sate(Ctx*, const EstArgs&);
 
 static int est_common(gpslc_ctx* h, int loc, const gpslc_data* d, const double* samples, int n_outer, int n_chains, int stride,
                       const int* ret_idx, int R, const double* doT, int n_doT, double jitter, int spp, uint64_t seed,
-                      int chain_offset, int var_as_std, bool sate, double* o1, double* o2, double* o3, int* info, int dot_offset = 0) {
+                      int chain_offset, int var_as_std, bool sate, double* o1, double* o2, double* o3, int* info, int dot_offset = 0,
+                      double summary_ci = 0.0, double* summary = nullptr) {
     if (!h) return GPSLC_ERR_ARG;
     Ctx* ctx = &h->c;
     if (!d || !samples || !ret_idx || !doT || d->n <= 0 || R < 0 || n_doT < 0 || n_chains <= 0 || spp < 0)
@@ -355,7 +357,18 @@ static int est_common(gpslc_ctx* h, int loc, const gpslc_data* d, const double* 
     GP_TRY(dInfo.outbuf(loc, info, tasks));
     a.info = dInfo.d;
     int rc;
-    if (!sate) {
+    Staged<double> dSum(ctx);
+    if (!sate && summary) {
+        // fused predictCounterfactualEffects + summarizeEstimates: the draws live only in the library's device arena
+        if (spp <= 0) return ctx->fail(GPSLC_ERR_ARG, "gpslc_ite_summary: samplesPerPosterior must be positive");
+        double* draws = nullptr;
+        GP_CUDA(ctx, ctx->arena_alloc(reinterpret_cast<void**>(&draws), tasks * spp * n * sizeof(double)));
+        GP_TRY(dSum.outbuf(loc, summary, (size_t)n_doT * n_chains * n * 3));
+        a.mean_out = nullptr; a.cov_out = nullptr; a.ite_out = draws;
+        rc = launch_ite(ctx, a);
+        if (!rc) rc = launch_summarize(ctx, draws, n_doT * n_chains, R * spp, n, summary_ci, dSum.d);
+        if (!rc) rc = dSum.finish();
+    } else if (!sate) {
         GP_TRY(d1.outbuf(loc, o1, tasks * n));
         GP_TRY(d2.outbuf(loc, o2, tasks * n * n));
         GP_TRY(d3.outbuf(loc, o3, tasks * spp * n));
@@ -387,6 +400,13 @@ int gpslc_ite_slice(gpslc_ctx* h, int loc, const gpslc_data* d, const double* sa
     if (dot_offset < 0) return GPSLC_ERR_ARG;
     return est_common(h, loc, d, samples, n_outer, n_chains, stride, ret_idx, R, doT, n_doT, jitter, spp, seed, chain_offset, 0,
                       false, meanITE, covITE, ite, info, dot_offset);
+}
+int gpslc_ite_summary(gpslc_ctx* h, int loc, const gpslc_data* d, const double* samples, int n_outer, int n_chains, int stride,
+                      const int* ret_idx, int R, const double* doT, int n_doT, int dot_offset, double jitter, int spp, uint64_t seed,
+                      int chain_offset, double credible_interval, double* summary, int* info) {
+    if (dot_offset < 0 || !summary || !(credible_interval > 0.0 && credible_interval < 1.0)) return GPSLC_ERR_ARG;
+    return est_common(h, loc, d, samples, n_outer, n_chains, stride, ret_idx, R, doT, n_doT, jitter, spp, seed, chain_offset, 0,
+                      false, nullptr, nullptr, nullptr, info, dot_offset, credible_interval, summary);
 }
 int gpslc_sate_slice(gpslc_ctx* h, int loc, const gpslc_data* d, const double* samples, int n_outer, int n_chains, int stride,
                      const int* ret_idx, int R, const double* doT, int n_doT, int dot_offset, double jitter, int spp, uint64_t seed,

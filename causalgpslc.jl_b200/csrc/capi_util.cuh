@@ -38,7 +38,7 @@ struct Staged {
 
 #define GP_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 
-__global__ void inv_sq_kernel(const double* ls, double* w, size_t n);
-int launch_inv_sq(Ctx* ctx, const double* ls, double* w, size_t n);
+__global__ void inv_sq_kernel(const double* ls, double* w, size_t n, int square);
+int launch_inv_sq(Ctx* ctx, const double* ls, double* w, size_t n, int square);
 
 }  // namespace gpslc

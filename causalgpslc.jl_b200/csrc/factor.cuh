@@ -463,11 +463,104 @@ __device__ __noinline__ void row_tile_kloop(double* __restrict__ accio, const do
 #endif
 }
 
+// Diagonal-tile slot of warp `warp` (see factor_run): the 36 lower 8x8 tiles of a diagonal block are dealt 5/4 to the warps —
+// warps p and p+4 share the row-tile pair (p, 7-p), which has 9 tiles: warp p takes row p and the first 4-p tiles of row 7-p,
+// warp p+4 the other four. Slot sl of a warp is tile (row, col).
+constexpr int DSLOTS = 5;
+__device__ __forceinline__ void diag_slot(const int warp, const int sl, int& row, int& col) {
+    const int pw = warp & 3;
+    if (warp < 4) { row = (sl <= pw) ? pw : 7 - pw; col = (sl <= pw) ? sl : sl - pw - 1; }
+    else { row = 7 - pw; col = min(4 - pw + sl, 7); }
+}
+
+// The k-loop of the FIRST row tile of panel j with the diagonal tile of the same panel folded in: the B slabs of a row tile are
+// the slabs of block row j, which are both operands of C_jj -= L_jJ L_jJ^T and the matrix of the forward-solve update
+// w_j -= L_jJ z_J. Folding saves the separate diagonal pass over the same slabs (its pipeline fill and drain, its barrier rounds,
+// one re-read of j*32 KB) and runs the 36 diagonal tiles at the row tiles' pipe utilisation. The operand pipeline covers this
+// tile only (F = T), so that the stage buffers are idle afterwards and P2 can alias them.
+// accio: [MI*16] row accumulators, then [2*DSLOTS] diagonal accumulators, then [MAXRHS] partial sums of L_jJ z_J (per thread:
+// row tid/4, k columns tid%4 + 4i).
+template <int MI>
+__device__ __noinline__ void row_tile_kloop_fold(double* __restrict__ accio, const double* __restrict__ scratch,
+                                                 const double* __restrict__ zbuf, const int npad, const int nrhs, const int j, const int T,
+                                                 const int blk0, const int blk_end, const uint32_t gi0) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FactorSmem& sm = *reinterpret_cast<FactorSmem*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int half = (MI == 2) ? (warp >> 2) : 0;
+    const int r8base = (MI == 2) ? (warp & 3) * 2 : warp;
+    double acc[MI][8][2];
+#pragma unroll
+    for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 8; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+    double dacc[DSLOTS][2];
+    int offa[DSLOTS], offb[DSLOTS];
+    const int nslots = (warp < 4) ? 5 : 4;
+#pragma unroll
+    for (int sl = 0; sl < DSLOTS; sl++) {
+        dacc[sl][0] = 0.0; dacc[sl][1] = 0.0;
+        int r, c;
+        diag_slot(warp, sl, r, c);
+        offa[sl] = r * (K4S * 32) + lane; offb[sl] = c * (K4S * 32) + lane;
+    }
+    double wsum[MAXRHS] = {0.0, 0.0};
+    const int wr = threadIdx.x >> 2, kq = threadIdx.x & 3;
+    const int loff = (wr >> 3) * (K4S * 32) + (wr & 7) * 4;
+    uint32_t gi = gi0;
+    for (int t = 0; t < T; t++, gi++) {
+        const int st = gi % STAGES;
+        mbar_wait(&sm.full[st], (gi / STAGES) & 1);
+        const double* sA = sm.stage + st * STAGE_D + half * SLAB_D + r8base * (K4S * 32);
+        const double* sB = sm.stage + st * STAGE_D + 2 * SLAB_D;
+#pragma unroll
+        for (int k4 = 0; k4 < K4S; k4++) {
+            double a[MI];
+#pragma unroll
+            for (int mi = 0; mi < MI; mi++) a[mi] = sA[mi * (K4S * 32) + k4 * 32 + lane];
+#pragma unroll
+            for (int ni = 0; ni < 8; ni++) {
+                const double b = sB[(ni * K4S + k4) * 32 + lane];
+#pragma unroll
+                for (int mi = 0; mi < MI; mi++) dmma(acc[mi][ni], a[mi], b);
+            }
+#pragma unroll
+            for (int sl = 0; sl < DSLOTS; sl++)
+                if (sl < nslots) dmma(dacc[sl], sB[offa[sl] + k4 * 32], sB[offb[sl] + k4 * 32]);
+        }
+        if (nrhs > 0) {
+#pragma unroll
+            for (int kk = 0; kk < KB / 4; kk++) {
+                const int kc = kq + 4 * kk;
+                const double l = sB[loff + (kc >> 2) * 32 + (kc & 3)];
+                for (int rh = 0; rh < nrhs; rh++) wsum[rh] = fma(l, zbuf[(size_t)rh * npad + t * KB + kc], wsum[rh]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0 && stage_release_is_last(&sm.freed[st]) && t + STAGES < T)
+            issue_row_slab(sm, scratch, j, T, blk0, blk_end, 0, t + STAGES, gi + STAGES);
+    }
+#pragma unroll
+    for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 8; ni++) {
+            accio[(mi * 8 + ni) * 2] = acc[mi][ni][0];
+            accio[(mi * 8 + ni) * 2 + 1] = acc[mi][ni][1];
+        }
+#pragma unroll
+    for (int sl = 0; sl < DSLOTS; sl++) { accio[MI * 16 + 2 * sl] = dacc[sl][0]; accio[MI * 16 + 2 * sl + 1] = dacc[sl][1]; }
+    accio[MI * 16 + 2 * DSLOTS] = wsum[0];
+    accio[MI * 16 + 2 * DSLOTS + 1] = wsum[1];
+}
+
 // Gen concept:
 //   void quad(int r0, int r1, int c, double& v00, double& v01, double& v10, double& v11) const
 //        -> K[r0][c], K[r0][c+1], K[r1][c], K[r1][c+1]   (lower triangle / rectangular rows; c even)
 //   double rhs(int which, int r) const
-template <class Gen, int TEAM = 0, bool SNAP = false>
+#ifndef GPSLC_FOLD
+#define GPSLC_FOLD 1    // 0: development A/B switch, separate diagonal k-loop everywhere
+#endif
+template <class Gen, int TEAM = 0, bool SNAP = false, bool FOLD = (GPSLC_FOLD != 0) && !SNAP>
 __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const int nrhs, double* scratch,
                            double* zbuf /* [MAXRHS][NCB*NB] solves, then [MAXRHS][NCB*NB] pre-solve w */,
                            FactorSmem& sm, Pipe& pipe, const int snapJ = 1 << 30, double* snap = nullptr, const int snap_n = 0) {
@@ -485,19 +578,27 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
     GP_PHASE_INIT();
     for (int j = 0; j < NCB; j++) {
         const int T = j * NSLAB;  // slabs in the k-loop of this panel
+        // Row blocks below the diagonal that this CTA owns. Team mode: the nblk blocks are dealt out in contiguous runs, the ranks
+        // that get one block more rotate with the panel index.
+        int nblk = NRB - j - 1, blk0 = j + 1;
+        if constexpr (TEAM != 0) {
+            const int er = (trank + j) % tsize, per = nblk / tsize, rem = nblk - per * tsize;
+            blk0 += er * per + min(er, rem);
+            nblk = per + (er < rem ? 1 : 0);
+        }
+        int blk_end = blk0 + nblk;
+        // FOLD: the diagonal tile's k-loop rides on the k-loop of this CTA's first row tile (row_tile_kloop_fold) whenever there is
+        // one; the accumulators of that tile wait in accm (local memory) while P2 runs and its epilogue follows P2.
+        const bool fold = FOLD && j > 0 && nblk > 0;
+        const bool fold2 = fold && (blk0 + 1 < blk_end);      // the folded tile has two blocks (128 rows)
+        double accm[2 * 16 + 2 * DSLOTS + MAXRHS];
         // =================================================================== diagonal tile
         {
-            // The 36 lower 8x8 tiles of the diagonal block are dealt 5/4 to the warps (instead of w+1 to warp w): warps p and
-            // p+4 share the row-tile pair (p, 7-p), which has 9 tiles: warp p takes row p and the first 4-p tiles of row 7-p,
-            // warp p+4 the other four. Slot s of a warp is tile (srow[s], scol[s]).
-            constexpr int DSLOTS = 5;
-            const int pw = warp & 3, nslots = (warp < 4) ? 5 : 4;
+            // the 36 lower 8x8 tiles of the diagonal block are dealt 5/4 to the warps (diag_slot); slot s of a warp is tile (srow[s], scol[s])
+            const int nslots = (warp < 4) ? 5 : 4;
             int srow[DSLOTS], scol[DSLOTS];
 #pragma unroll
-            for (int sl = 0; sl < DSLOTS; sl++) {
-                if (warp < 4) { srow[sl] = (sl <= pw) ? pw : 7 - pw; scol[sl] = (sl <= pw) ? sl : sl - pw - 1; }
-                else { srow[sl] = 7 - pw; scol[sl] = min(4 - pw + sl, 7); }
-            }
+            for (int sl = 0; sl < DSLOTS; sl++) diag_slot(warp, sl, srow[sl], scol[sl]);
             double acc[DSLOTS][2];
 #pragma unroll
             for (int sl = 0; sl < DSLOTS; sl++) { acc[sl][0] = 0.0; acc[sl][1] = 0.0; }
@@ -519,9 +620,17 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                 bulk_g2s(sm.stage + st * STAGE_D + SLAB_D, scratch + row_off(j) + (size_t)t2 * DS * SLAB_D, DS * SLAB_D * 8, &sm.full[st]);
 #endif
             };
-            for (int t2 = 0; t2 < STAGES && t2 < T2; t2++) {
-                const uint32_t gi = pipe.consumed + t2;
-                if (lane == 0 && warp == (int)(gi & (FWARPS - 1))) issue_diag_slab(t2, gi);
+            if (!fold) {
+                for (int t2 = 0; t2 < STAGES && t2 < T2; t2++) {
+                    const uint32_t gi = pipe.consumed + t2;
+                    if (lane == 0 && warp == (int)(gi & (FWARPS - 1))) issue_diag_slab(t2, gi);
+                }
+            } else {
+                // operand pipeline over the first row tile only (its B slabs are the diagonal block row's slabs)
+                for (int f = 0; f < STAGES && f < T; f++) {
+                    const uint32_t gi = pipe.consumed + f;
+                    if (lane == 0 && warp == (int)(gi & (FWARPS - 1))) issue_row_slab(sm, scratch, j, T, blk0, blk_end, 0, f, gi);
+                }
             }
             // column features of this panel for the generators, while the first operand copies are in flight; they are first
             // read after the barrier that follows the k-loop, and the previous panel's readers are behind its end-of-panel barrier
@@ -563,7 +672,17 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                     if (lane == 0 && stage_release_is_last(&sm.freed[st]) && t2 + STAGES < T2) issue_diag_slab(t2 + STAGES, gi + STAGES);
                 }
             };
-            kloop(0, Tsnap / DS);
+            if (!fold) {
+                kloop(0, Tsnap / DS);
+            } else {
+                if (fold2) row_tile_kloop_fold<2>(accm, scratch, zbuf, npad, nrhs, j, T, blk0, blk_end, pipe.consumed);
+                else row_tile_kloop_fold<1>(accm, scratch, zbuf, npad, nrhs, j, T, blk0, blk_end, pipe.consumed);
+                pipe.consumed += T;
+                const int ao = fold2 ? 32 : 16;
+#pragma unroll
+                for (int sl = 0; sl < DSLOTS; sl++) { acc[sl][0] = accm[ao + 2 * sl]; acc[sl][1] = accm[ao + 2 * sl + 1]; }
+                wsum[0] = accm[ao + 2 * DSLOTS]; wsum[1] = accm[ao + 2 * DSLOTS + 1];
+            }
             if constexpr (SNAP) {
                 if (in_tail) {
                     wsnap[0] = wsum[0]; wsnap[1] = wsum[1];
@@ -652,35 +771,19 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
             GP_PHASE_MARK(6);
         }
         // =================================================================== row tiles below the diagonal
-        // Blocks j+1.. are processed two at a time (128-row tiles, warp w owns rows 16w..16w+15); an odd leftover block is
+        // Blocks blk0.. are processed two at a time (128-row tiles, warp w owns rows 16w..16w+15); an odd leftover block is
         // processed as a 64-row tile (warp w owns rows 8w..8w+7) so that it costs half a tile of tensor time, not a full one.
-        // team mode: the nblk blocks below the diagonal are dealt out in contiguous runs, the ranks that get one block more
-        // rotate with the panel index
-        int nblk = NRB - j - 1, blk0 = j + 1;
-        if constexpr (TEAM != 0) {
-            const int er = (trank + j) % tsize, per = nblk / tsize, rem = nblk - per * tsize;
-            blk0 += er * per + min(er, rem);
-            nblk = per + (er < rem ? 1 : 0);
-        }
-        const int blk_end = blk0 + nblk;
-        const int ntile = (nblk + 1) >> 1;
-        const int F = ntile * T;
-        // prologue of the operand pipeline: the first STAGES slabs of the panel (the k-loops issue the rest as they go)
-        for (int f = 0; f < STAGES && f < F; f++) {
-            const uint32_t gi = pipe.consumed + f;
-            if (lane == 0 && warp == (int)(gi & (FWARPS - 1))) issue_row_slab(sm, scratch, j, T, blk0, blk_end, f / T, f % T, gi);
-        }
         // slab index at which the Schur-complement snapshot is taken, or -1 (parameters live in shared memory)
         const int Tsnap = (SNAP && snap != nullptr && j >= snapJ) ? snapJ * NSLAB : -1;
-        // MI = 2: 128-row tile (blocks I0, I0+1); MI = 1: 64-row tile (block I0 only)
-        auto run_tile = [&](auto mi_tag, const int tile) {
+        // MI = 2: 128-row tile (blocks I0, I0+1); MI = 1: 64-row tile (block I0 only). do_kloop = false: the accumulators are
+        // already in accm (the folded first tile).
+        auto run_tile = [&](auto mi_tag, const int tile, const bool do_kloop, const int F) {
             constexpr int MI = decltype(mi_tag)::value;
             const int I0 = blk0 + 2 * tile;
             const int half = (MI == 2) ? (warp >> 2) : 0;
             const int I = I0 + half;                                   // block this warp works on
             const int r8base = (MI == 2) ? (warp & 3) * 2 : warp;      // first 8-row group of this warp inside block I
-            double accm[MI * 16];                                      // local memory: filled by the non-inlined k-loop
-            double acc[MI][8][2];
+            double acc[MI][8][2];                                      // accm (local memory) is filled by the non-inlined k-loop
             const int r0 = I * NB + r8base * 8 + g;
             auto kloop = [&](const int tb, const int te) {
                 row_tile_kloop<MI>(accm, scratch, j, T, blk0, blk_end, tile, F, tb, te, pipe.consumed);
@@ -726,7 +829,7 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                     kloop(Ts, T);
                 }
             } else {
-                kloop(0, T);
+                if (do_kloop) kloop(0, T);
             }
             GP_PHASE_MARK(2);
             fetch_acc();
@@ -784,9 +887,25 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                 }
             }
         };
-        for (int tile = 0; tile < ntile; tile++) {
-            if (blk0 + 2 * tile + 1 < blk_end) run_tile(std::integral_constant<int, 2>{}, tile);
-            else run_tile(std::integral_constant<int, 1>{}, tile);
+        if (fold) {
+            // epilogue of the folded first tile (its k-loop ran before P2), then the remaining tiles as a panel of their own
+            if (fold2) run_tile(std::integral_constant<int, 2>{}, 0, false, 0);
+            else run_tile(std::integral_constant<int, 1>{}, 0, false, 0);
+            blk0 = min(blk0 + 2, blk_end);
+            nblk = blk_end - blk0;
+        }
+        {
+            const int ntile = (nblk + 1) >> 1;
+            const int F = ntile * T;
+            // prologue of the operand pipeline: the first STAGES slabs (the k-loops issue the rest as they go)
+            for (int f = 0; f < STAGES && f < F; f++) {
+                const uint32_t gi = pipe.consumed + f;
+                if (lane == 0 && warp == (int)(gi & (FWARPS - 1))) issue_row_slab(sm, scratch, j, T, blk0, blk_end, f / T, f % T, gi);
+            }
+            for (int tile = 0; tile < ntile; tile++) {
+                if (blk0 + 2 * tile + 1 < blk_end) run_tile(std::integral_constant<int, 2>{}, tile, true, F);
+                else run_tile(std::integral_constant<int, 1>{}, tile, true, F);
+            }
         }
         pipe.produced = pipe.consumed;   // everything issued for this panel has been consumed
         GP_PHASE_MARK(3);

@@ -66,7 +66,7 @@ int pick_team(Ctx* ctx, long long tasks, int NCB) {
 // ------------------------------------------------------------------------------------------------ cov build
 // Materialised covariance (HBM-bound): K[b] (n x n, column-major) for `batch` parameter sets. One thread computes a
 // 1x4 strip of a column block so that stores are 32-byte vectors along the fastest (row) dimension.
-// feat: [batch or 1][D][n] feature columns (row-contiguous), w: [batch][D], scale/noise: [batch].
+// feat: [batch or 1][D][n] feature columns (row-contiguous), w: [batch][D] = 1 / lengthscale, scale/noise: [batch].
 // X2 != X1 is supported (likelihood.jl:27 builds K(T, doT)).
 __global__ void __launch_bounds__(256) cov_build_kernel(int n, int D, const double* __restrict__ f1, const double* __restrict__ f2,
                                                         size_t feat_stride, const double* __restrict__ w,
@@ -86,11 +86,11 @@ __global__ void __launch_bounds__(256) cov_build_kernel(int n, int D, const doub
     if (threadIdx.x < 32) tab[threadIdx.x] = GPSLC_EXP2_TAB[threadIdx.x];
     for (int i = threadIdx.x; i < D * 32; i += blockDim.x) {
         const int d = i >> 5, c = c0 + (i & 31);
-        sc[i] = (c < n) ? p2[(size_t)d * n + c] * sqrt(w[(size_t)b * D + d]) : 0.0;
+        sc[i] = (c < n) ? p2[(size_t)d * n + c] * w[(size_t)b * D + d] : 0.0;
     }
     for (int i = threadIdx.x; i < D * 128; i += blockDim.x) {
         const int d = i >> 7, r = r0 + (i & 127);
-        sr[i] = (r < n) ? p1[(size_t)d * n + r] * sqrt(w[(size_t)b * D + d]) : 0.0;
+        sr[i] = (r < n) ? p1[(size_t)d * n + r] * w[(size_t)b * D + d] : 0.0;
     }
     __syncthreads();
     const double s = scale[b];
@@ -140,14 +140,21 @@ __global__ void __launch_bounds__(256) cov_build_kernel(int n, int D, const doub
     }
 }
 
-// K(X, X): the matrix is symmetric, so only the tiles on and below the block diagonal are computed (half the FP64 work, which is
-// what keeps this kernel off the HBM roofline at D ~ 12) and every off-diagonal tile is written twice, once as it is and once
-// transposed through shared memory so that both stores are coalesced along the fastest (row) dimension. 64 x 64 tiles, one per
-// CTA, 4 x 4 entries per thread. K comes out exactly symmetric.
-__global__ void __launch_bounds__(256) cov_build_sym_kernel(int n, int D, const double* __restrict__ f, size_t feat_stride,
-                                                            const double* __restrict__ w, const double* __restrict__ scale,
-                                                            const double* __restrict__ noise, int has_noise, double* __restrict__ K) {
-    extern __shared__ double sh[];  // [32] 2^(i/32) table, [D][64] column features, [D][64] row features, [64][65] transpose tile
+// K(X, X): the matrix is symmetric, so only the 64 x 64 tiles on and below the block diagonal are computed (half the FP64 work:
+// at D ~ 12 an entry costs 2 D + 12 FP64-pipe instructions, which is what keeps a one-sided kernel off the HBM roofline) and every
+// off-diagonal tile is written twice, as it is and transposed. Both stores come straight from the 4 x 4 register block of a thread
+// as 32-byte sector-aligned pieces (streaming stores, evict-first): the direct store is contiguous along a column, the transposed
+// one writes one full sector per (thread, row) — L2 assembles the lines, no shared-memory transpose, no barrier after the feature
+// staging, 12.5 KB of shared memory and <= 64 registers, so four CTAs are resident per SM. K comes out exactly symmetric.
+__device__ __forceinline__ void store4_cs(double* dst, const double (&v)[4]) {
+    __stcs(reinterpret_cast<double2*>(dst), make_double2(v[0], v[1]));
+    __stcs(reinterpret_cast<double2*>(dst) + 1, make_double2(v[2], v[3]));
+}
+
+__global__ void __launch_bounds__(256, 4) cov_build_sym_kernel(int n, int D, const double* __restrict__ f, size_t feat_stride,
+                                                               const double* __restrict__ w, const double* __restrict__ scale,
+                                                               const double* __restrict__ noise, int has_noise, double* __restrict__ K) {
+    extern __shared__ __align__(16) double sh[];  // [32] 2^(i/32) table, [D][64] column features, [D][64] row features
     const int b = blockIdx.z;
     // linear index of a lower-triangular tile pair -> (bi >= bj)
     const int p = blockIdx.x;
@@ -159,12 +166,11 @@ __global__ void __launch_bounds__(256) cov_build_sym_kernel(int n, int D, const 
     double* tab = sh;
     double* sc = sh + 32;
     double* sr = sc + D * 64;
-    double* tile = sr + D * 64;
     const double* pf = f + (size_t)b * feat_stride;
     if (threadIdx.x < 32) tab[threadIdx.x] = GPSLC_EXP2_TAB[threadIdx.x];
     for (int i = threadIdx.x; i < D * 64; i += blockDim.x) {
         const int d = i >> 6, o = i & 63;
-        const double sw = sqrt(w[(size_t)b * D + d]);
+        const double sw = w[(size_t)b * D + d];     // 1 / lengthscale
         sc[i] = (c0 + o < n) ? pf[(size_t)d * n + c0 + o] * sw : 0.0;
         sr[i] = (r0 + o < n) ? pf[(size_t)d * n + r0 + o] * sw : 0.0;
     }
@@ -172,17 +178,16 @@ __global__ void __launch_bounds__(256) cov_build_sym_kernel(int n, int D, const 
     const double s = scale[b];
     const double nz = has_noise ? noise[b] : 0.0;
     const int tr = (threadIdx.x & 15) * 4, tc = (threadIdx.x >> 4) * 4;
-    double acc[4][4];
+    double acc[4][4];       // [column j][row i]
 #pragma unroll
     for (int j = 0; j < 4; j++)
 #pragma unroll
         for (int i = 0; i < 4; i++) acc[j][i] = 0.0;
+#pragma unroll 2
     for (int d = 0; d < D; d++) {
-        double zr[4], zc[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) zr[i] = sr[d * 64 + tr + i];
-#pragma unroll
-        for (int j = 0; j < 4; j++) zc[j] = sc[d * 64 + tc + j];
+        const double2 ra = *reinterpret_cast<const double2*>(sr + d * 64 + tr), rb = *reinterpret_cast<const double2*>(sr + d * 64 + tr + 2);
+        const double2 ca = *reinterpret_cast<const double2*>(sc + d * 64 + tc), cb = *reinterpret_cast<const double2*>(sc + d * 64 + tc + 2);
+        const double zr[4] = {ra.x, ra.y, rb.x, rb.y}, zc[4] = {ca.x, ca.y, cb.x, cb.y};
 #pragma unroll
         for (int j = 0; j < 4; j++)
 #pragma unroll
@@ -191,45 +196,39 @@ __global__ void __launch_bounds__(256) cov_build_sym_kernel(int n, int D, const 
                 acc[j][i] = fma(t, t, acc[j][i]);
             }
     }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            acc[j][i] = fma(s, exp_neg_tab(acc[j][i], tab), (has_noise && (r0 + tr + i) == (c0 + tc + j)) ? nz : 0.0);
     double* Kb = K + (size_t)b * n * n;
     const bool vec_ok = ((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(Kb) & 31) == 0);
+    // direct: column c0+tc+j, rows r0+tr .. +3
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const int c = c0 + tc + j;
-        double v[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            v[i] = fma(s, exp_neg_tab(acc[j][i], tab), (has_noise && (r0 + tr + i) == c) ? nz : 0.0);
-            tile[(tr + i) * 65 + tc + j] = v[i];
-        }
-        if (c < n) {
-            const int r = r0 + tr;
-            double* dst = Kb + (size_t)c * n + r;
-            if (vec_ok && r + 3 < n) *reinterpret_cast<double4*>(dst) = make_double4(v[0], v[1], v[2], v[3]);
-            else {
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-                    if (r + i < n) dst[i] = v[i];
-            }
-        }
-    }
-    if (bi == bj) return;
-    __syncthreads();
-    // transposed tile: output column = a row of this tile, output rows = its columns
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int cc = r0 + tc + j;              // global column of the transposed block (a row index of this tile)
-        if (cc >= n) continue;
-        const int rr = c0 + tr;                  // global rows: the tile's columns
-        double v[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) v[i] = tile[(tc + j) * 65 + tr + i];
-        double* dst = Kb + (size_t)cc * n + rr;
-        if (vec_ok && rr + 3 < n) *reinterpret_cast<double4*>(dst) = make_double4(v[0], v[1], v[2], v[3]);
+        const int c = c0 + tc + j, r = r0 + tr;
+        if (c >= n) continue;
+        double* dst = Kb + (size_t)c * n + r;
+        if (vec_ok && r + 3 < n) store4_cs(dst, acc[j]);
         else {
 #pragma unroll
             for (int i = 0; i < 4; i++)
-                if (rr + i < n) dst[i] = v[i];
+                if (r + i < n) dst[i] = acc[j][i];
+        }
+    }
+    if (bi == bj) return;
+    // transposed: column r0+tr+i (a row of this tile), rows c0+tc .. +3 (its columns)
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int cc = r0 + tr + i, rr = c0 + tc;
+        if (cc >= n) continue;
+        const double v[4] = {acc[0][i], acc[1][i], acc[2][i], acc[3][i]};
+        double* dst = Kb + (size_t)cc * n + rr;
+        if (vec_ok && rr + 3 < n) store4_cs(dst, v);
+        else {
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++)
+                if (rr + jj < n) dst[jj] = v[jj];
         }
     }
 }
@@ -239,8 +238,7 @@ int launch_cov_build(Ctx* ctx, int n, int batch, int D, const double* f1, const 
     if (f1 == f2) {
         const int nt = ceil_div(n, 64);
         dim3 grid(nt * (nt + 1) / 2, 1, batch);
-        const size_t sh = (size_t)(32 + 2 * D * 64 + 64 * 65) * sizeof(double);
-        GP_CUDA(ctx, cudaFuncSetAttribute(cov_build_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+        const size_t sh = (size_t)(32 + 2 * D * 64) * sizeof(double);
         cov_build_sym_kernel<<<grid, 256, sh, ctx->stream>>>(n, D, f1, feat_stride, w, scale, noise, noise != nullptr, K);
         ctx->launches++;
         GP_CUDA(ctx, cudaGetLastError());

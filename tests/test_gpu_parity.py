@@ -184,7 +184,8 @@ def test_sampler_reproduces_oracle_chain(ctx, n, n_obj, nX, nU, with_u, binary):
                 assert abs(lp0[c, f] - want) <= 1e-10 * abs(want)
         for k in range(md.spec.nU):
             qw, _ = om.u_prior_quad_logdet(st.U[k], counts, md.eps, md.cov)
-            assert abs(q0[c, k] - qw) <= 1e-6 * abs(qw)        # limited by the 1e-13-scale deviations inside an object
+            assert abs(q0[c, k] - qw) <= 1e-9 * abs(qw)        # closed form on both sides; the (u - mean)^2 / 1e-13 term cancels ~7 digits
+                                                               # (a dense LAPACK evaluation of the same quantity is only 1e-6 accurate)
         stats = {}
         want, _ = oi.posterior(md, nOuter, nMH, nES, seed=seed, chain=c, stats=stats)
         assert np.array_equal(stats["accepts"], acc[c].astype(np.int64))
@@ -231,6 +232,85 @@ def test_sampler_option_switches(ctx):
         assert want.shape[1] == got.shape[2] and np.allclose(np.nan_to_num(want), np.nan_to_num(got[:, c, :]), rtol=1e-9, atol=1e-12)
 
 
+def test_sampler_dense_sigma_u_matches_oracle(ctx):
+    """`samplePosterior(hyperparams, priorparams, SigmaU, X, T, Y)` accepts ANY SigmaU (src/driver.jl:59-69; generateU factors
+    uNoise*SigmaU, src/model_prior.jl:27-30). A matrix that is not a generateSigmaU block matrix goes through
+    gpslc_data.sigma_u_dense: factored once on the device, U prior density by forward substitution, draws L_S z. Chains must
+    reproduce the oracle's Cholesky-based chain; real and binary T, ragged n (two 64-blocks), nU = 2 as well."""
+    for n, nX, nU, binary in ((100, 2, 1, False), (70, 1, 2, True)):
+        counts, X, T, Y = od.synthetic(n, 2, nX, seed=13)
+        if binary:
+            T = T > np.median(T)
+        i = np.arange(n)
+        S = 0.5 * np.exp(-np.abs(i[:, None] - i[None, :]) / 5.0) + 0.6 * np.eye(n)
+        pri = {**g.getPriorParameters(), "SigmaU": S}
+        md = od.model_data_from_arrays(None, X, T, Y, nU=nU, sigma_u_dense=S)
+        s = ChainSampler(pri, X, T, Y, nU, None, 3, 2, 2, n_chains=3, seed=31, ctx=ctx)
+        st0 = s.state(); lp0, q0 = s.terms()
+        s.run(3)
+        got = s.samples(); acc, ev = s.stats()
+        s.close()
+        L = np.linalg.cholesky(S)
+        for c in range(3):
+            st = oi.generate_initial_state(md, 31, c)
+            assert np.allclose(np.nan_to_num(oi.pack_sample(md.spec, st)), np.nan_to_num(st0[c]), rtol=1e-10, atol=1e-12)
+            for k in range(nU):
+                z = np.linalg.solve(L, st.U[k])
+                assert abs(q0[c, k] - z @ z) <= 1e-11 * (z @ z)
+            stats = {}
+            want, _ = oi.posterior(md, 3, 2, 2, seed=31, chain=c, stats=stats)
+            assert np.array_equal(stats["accepts"], acc[c].astype(np.int64)) and stats["ess_evals"] == int(ev[c])
+            assert np.allclose(np.nan_to_num(want), np.nan_to_num(got[:, c, :]), rtol=1e-8, atol=1e-11)
+    # a SigmaU that is not positive definite is the PosDefException generateU would throw
+    bad = np.eye(20); bad[5, 5] = -1.0
+    counts, X, T, Y = od.synthetic(20, 2, 1, seed=1)
+    with pytest.raises(g.GpslcError) as ei:
+        ChainSampler({**g.getPriorParameters(), "SigmaU": bad}, X, T, Y, 1, None, 1, 1, 1, ctx=ctx)
+    assert ei.value.code == 3
+
+
+def test_binary_chain_with_textbook_slice_rule_and_small_prior_shapes(ctx):
+    """ess_rule = 1 must apply to BOTH sliced addresses (U_k and logitT: the logitT test then uses the Bernoulli terms only), and
+    InvGamma priors with shape < 1 go through the boosted gamma sampler; both against the oracle chain."""
+    counts, X, T, Y = od.synthetic(90, 3, 2, seed=19)
+    Tb = T > np.median(T)
+    md = od.model_data_from_arrays(counts, X, Tb, Y, nU=1)
+    *_, got, acc, ev = _run_pair(md, X, Tb, Y, counts, 3, 2, 2, 8, 2, ess_rule=1)
+    logit_evals = _run_pair.logit_evals.copy()
+    *_, got0, _, _ = _run_pair(md, X, Tb, Y, counts, 3, 2, 2, 8, 2, ess_rule=0)
+    assert not np.array_equal(got, got0)
+    for c in range(2):
+        stats = {}
+        want, _ = oi.posterior(md, 3, 2, 2, seed=8, chain=c, ess_rule="likelihood_only", stats=stats)
+        assert stats["ess_evals_logit"] == int(logit_evals[c])
+        assert np.allclose(np.nan_to_num(want), np.nan_to_num(got[:, c, :]), rtol=1e-8, atol=1e-11)
+    pri = {**g.getPriorParameters(), "tyLSShape": 0.5, "yNoiseShape": 0.9, "uNoiseShape": 0.35}
+    md = od.model_data_from_arrays(counts, X, T, Y, nU=1, prior=pri)
+    *_, got, acc, ev = _run_pair(md, X, T, Y, counts, 2, 2, 1, 5, 2)
+    for c in range(2):
+        want, _ = oi.posterior(md, 2, 2, 1, seed=5, chain=c)
+        assert np.allclose(np.nan_to_num(want), np.nan_to_num(got[:, c, :]), rtol=1e-8, atol=1e-11)
+    for bad in ({"tyLSShape": 0.0}, {"yScaleScale": -1.0}, {"drift": 0.0}, {"xtLSShape": float("nan")}):
+        with pytest.raises(g.GpslcError) as ei:
+            ChainSampler({**g.getPriorParameters(), **bad}, X, T, Y, 1, counts, 1, 1, 1, ctx=ctx)
+        assert ei.value.code == 2
+
+
+def test_non_pd_prediction_raises_like_the_reference(ctx):
+    """A posterior sample whose Kp = Kww + yNoise*I is not positive definite makes `\\` / `mvnormal` throw PosDefException in the
+    reference (src/likelihood.jl:42-43, src/estimation.jl:105); the drivers must not hand back garbage draws."""
+    counts, X, T, Y = od.synthetic(40, 4, 2, seed=6)
+    h = g.getHyperParameters(); h.nOuter, h.nBurnIn = 4, 2
+    gobj = g.gpslc(counts, X, T, Y, hyperparams=h, ctx=ctx)
+    assert g.sampleITE(gobj, 0.3, ctx=ctx).shape == (40, 30)
+    gobj.posteriorPacked[2, 0, 2] = -50.0           # yNoise of the second retained sample
+    for fn in (lambda: g.sampleITE(gobj, 0.3, ctx=ctx), lambda: g.sampleSATE(gobj, 0.3, ctx=ctx), lambda: g.ITEDistributions(gobj, 0.3, ctx=ctx),
+               lambda: g.SATEDistributions(gobj, 0.3, ctx=ctx), lambda: g.predictCounterfactualEffects(gobj, 2, fidelity=3, ctx=ctx)):
+        with pytest.raises(g.PosDefException) as ei:
+            fn()
+        assert ei.value.info >= 1 and "retained sample 1" in str(ei.value)
+
+
 def test_chain_sharding_is_invariant(ctx):
     """Chains 2,3 of a 4-chain run == a 2-chain run with chain_offset=2 (multi-GPU sharding)."""
     counts, X, T, Y = od.synthetic(80, 4, 2, seed=3)
@@ -260,6 +340,72 @@ def test_incremental_caches_stay_consistent_at_c3_shape(ctx):
     state = om.State(st[0, :md.spec.n_params].copy(), st[0, md.spec.n_params:].reshape(1, 1024).copy())
     want = om.factor_logpdf(md, state, 11)
     assert abs(lp[0, 11] - want) <= 1e-10 * abs(want)
+
+
+@pytest.mark.timeout(600)
+def test_chain_reproduces_oracle_at_c3_size(ctx):
+    """BASELINE c3 shape (n=1024, 16 objects, nX=10, nU=1): one full default outer iteration — 10 MH sweeps of 58 sites with
+    identical accept decisions + 5 elliptical-slice passes — of the CUDA chain against the oracle chain driven by the same Philox
+    streams (the oracle needs ~25 s per chain on the host)."""
+    n, n_obj, nX = 1024, 16, 10
+    counts, X, T, Y = od.synthetic(n, n_obj, nX, seed=1234)
+    md = od.model_data_from_arrays(counts, X, T, Y, nU=1)
+    s = ChainSampler(md.prior, X, T, Y, 1, counts, 1, 10, 5, n_chains=2, seed=77, ctx=ctx)
+    s.run(1); got = s.samples(); acc, ev = s.stats(); s.close()
+    stats = {}
+    want, _ = oi.posterior(md, 1, 10, 5, seed=77, chain=1, stats=stats)
+    assert np.array_equal(stats["accepts"], acc[1].astype(np.int64)) and stats["ess_evals"] == int(ev[1])
+    assert 150 < acc[1].sum() < 450
+    err = np.nanmax(np.abs(want - got[:, 1, :]) / (1e-9 + np.abs(want)))
+    print("c3-size chain: max relative deviation", err)
+    assert err < 1e-9
+
+
+@pytest.mark.timeout(600)
+def test_factor_logpdf_at_c4_size_vs_scipy_cholesky(ctx):
+    """BASELINE c4 size (n=4096, 64 objects, nX=10): the T and Y factor log-densities of a `generate`d state, computed by the
+    fused build + 64-panel Cholesky (here in cluster-team mode: one chain), against SciPy's LAPACK Cholesky of the oracle-built
+    covariance, rel 1e-10 (north_star's deterministic tolerance)."""
+    n, n_obj, nX = 4096, 64, 10
+    counts, X, T, Y = od.synthetic(n, n_obj, nX, seed=1234)
+    md = od.model_data_from_arrays(counts, X, T, Y, nU=1)
+    s = ChainSampler(md.prior, X, T, Y, 1, counts, 1, 1, 1, n_chains=1, seed=3, ctx=ctx)
+    st = s.state(); lp, q = s.terms(); s.close()
+    state = om.State(st[0, :md.spec.n_params].copy(), st[0, md.spec.n_params:].reshape(1, n).copy())
+    for f in (nX, nX + 1, 3):
+        want = om.factor_logpdf(md, state, f)
+        print("c4-size factor", f, lp[0, f], want)
+        assert abs(lp[0, f] - want) <= 1e-10 * abs(want)
+
+
+@pytest.mark.timeout(1500)
+def test_ite_at_c5_size_vs_reference_algebra(ctx):
+    """BASELINE c5 size (n=8192): MeanITE and SATE of one (posterior sample, doT) from the 16384 x 16384 augmented Cholesky (cluster
+    teams) against the oracle's line-by-line restatement of likelihood.jl / estimation.jl (two LU solves with n x n right-hand sides,
+    Bunch-Kaufman, four n x n products: ~1e13 flops on the host). The posterior sample is a SAMPLED one: a chain's state after one
+    outer iteration (1 MH sweep + 1 slice pass) at n=8192."""
+    n, n_obj, nX = 8192, 128, 10
+    counts, X, T, Y = od.synthetic(n, n_obj, nX, seed=1234)
+    s = ChainSampler(g.getPriorParameters(), X, T, Y, 1, counts, 1, 1, 1, n_chains=1, seed=5, ctx=ctx)
+    s.run(1); smp = s.samples(); acc, ev = s.stats(); s.close()
+    assert acc.sum() > 5 and ev[0] >= 1
+    ret = np.zeros(1, dtype=np.int32)
+    doT = 0.3
+    out = ge.ite(smp, X, T, Y, 1, [doT], ret, 1e-10, 2, seed=4, ctx=ctx)
+    so = ge.sate(smp, X, T, Y, 1, [doT], ret, 1e-10, 2, seed=4, ctx=ctx)
+    assert out["info"].max() == 0 and so["info"].max() == 0 and np.all(np.isfinite(out["samples"]))
+    spec = om.ModelSpec(n, 1, nX, False)
+    uyLS, xyLS, tyLS, yNoise, yScale, U = oe.extract_parameters(spec, smp[0, 0])
+    M, Cv = oe.conditional_ite(uyLS, xyLS, tyLS, yNoise, yScale, U, X, T, Y, doT)
+    assert np.max(np.abs(M - out["mean"][0, 0, 0])) <= 1e-8 * np.max(np.abs(M))
+    ms, vs = oe.conditional_sate(M, Cv)
+    vs += 1e-10 / n                                  # the jitter ITEDistributions adds to the diagonal (src/estimation.jl:82)
+    print("c5-size: MeanSATE", ms, so["mean"][0, 0, 0], "VarSATE", vs, so["var"][0, 0, 0])
+    assert abs(ms - so["mean"][0, 0, 0]) <= 1e-8 * max(abs(ms), np.max(np.abs(M)))
+    assert abs(vs - so["var"][0, 0, 0]) <= 1e-7 * abs(vs)
+    # the draws scatter around MeanITE with the posterior covariance: standardised by the oracle's diagonal they are O(1)
+    zs = (out["samples"][0, 0] - M[None, :]) / np.sqrt(np.maximum(np.diag(Cv), 1e-300))[None, :]
+    assert np.abs(zs).max() < 8.0 and 0.5 < zs.std() < 1.5
 
 
 def test_error_behaviour(ctx):
@@ -440,43 +586,78 @@ def test_public_api_shapes_and_golden_gate(ctx, kats):
     assert xyLS is None and U.shape == (150, 1) and tyLS > 0
 
 
-def _golden_match(ctx, name, doT, chains=16, seed=100):
-    """Per-chain (fraction of mean ITEs inside the golden 90 % interval, correlation of the mean ITEs with the golden means)."""
+# ---- the reference's 14 golden ITE summaries (test/test_results/*.csv). Only NEEC_sampled_0.6.csv is used by a reference test
+# (test/driver.jl:46-52); every file gets an asserted status here. Product configuration (ess_rule 0, current kernel convention,
+# default budget), 64 chains, seed 100 - the first row of each block of profiles/golden_table_r02.md, which also shows that no
+# combination of slice rule / lengthscale convention / 4x budget changes any verdict.
+#   gate   fraction of chains that pass the reference's own gate (>= 50 % of the individuals' mean ITE inside the golden 90 % interval)
+#   corr   median correlation of a chain's mean ITEs with the golden Mean column (None where the effects are inside the noise)
+#   mean / sd / width   chain-pooled summary statistics of BASELINE.md section 2: mean and sd over individuals of the mean ITE, mean CI width
+_GOLDEN_FITS = {}
+
+
+def _golden_stats(ctx, name, tag, chains=64, seed=100):
     import pandas as pd
-    gobj = g.gpslc(os.path.join(GOLD, "data", name + ".csv"), seed=seed, n_chains=chains, ctx=ctx)
-    assert g.getN(gobj) == 200 and gobj.X.shape == (200, 3) and len(gobj.posteriorSamples) == 24
-    ite = g.sampleITE(gobj, float(doT), all_chains=True, ctx=ctx)             # [C, n, R*spp]
-    assert ite.shape == (chains, 200, 150) and np.all(np.isfinite(ite))
-    exp = pd.read_csv(os.path.join(GOLD, "results", f"{name}_{doT}.csv"))
+    if name not in _GOLDEN_FITS:
+        _GOLDEN_FITS[name] = g.gpslc(os.path.join(GOLD, "data", name + ".csv"), seed=seed, n_chains=chains, ctx=ctx)
+    gobj = _GOLDEN_FITS[name]
+    assert len(gobj.posteriorSamples) == 24
+    doT = {"true": True, "false": False}.get(tag, None) if tag in ("true", "false") else float(tag)
+    ite = g.sampleITE(gobj, doT, all_chains=True, ctx=ctx)                    # [C, n, R*spp]
+    assert ite.shape == (chains, g.getN(gobj), 150) and np.all(np.isfinite(ite))
+    exp = pd.read_csv(os.path.join(GOLD, "results", f"{name}_{tag}.csv"))
+    lo, hi, gm = exp["LowerBound"].values, exp["UpperBound"].values, exp["Mean"].values
     means = ite.mean(axis=2)
-    inside = ((exp["LowerBound"].values[None] <= means) & (means <= exp["UpperBound"].values[None])).mean(axis=1)
-    corr = np.array([np.corrcoef(m, exp["Mean"].values)[0, 1] for m in means])
-    return inside, corr
+    inside = ((lo[None] <= means) & (means <= hi[None])).mean(axis=1)
+    corr = np.array([np.corrcoef(m, gm)[0, 1] for m in means])
+    q = np.quantile(ite, [0.05, 0.95], axis=2)
+    pooled = means.mean(axis=0)
+    return {"gate": float((inside >= 0.5).mean()), "corr": float(np.median(corr)), "mean": float(pooled.mean()), "sd": float(pooled.std(ddof=1)),
+            "width": float((q[1] - q[0]).mean()), "g_mean": float(gm.mean()), "g_sd": float(gm.std(ddof=1)), "g_width": float((hi - lo).mean())}
 
 
-@pytest.mark.parametrize("name,min_corr,all_pass_gate", [("multiplicative_linear", 0.9, True), ("multiplicative_nonlinear", 0.6, False),
-                                                         ("additive_nonlinear", 0.7, False)])
-def test_synthetic_golden_fixtures(ctx, name, min_corr, all_pass_gate):
-    """The reference ships four synthetic n=200 datasets (T, Y, X1..X3, obj) with golden ITE summaries at doT = 0 and 1
-    (test/test_results/<name>_{0,1}.csv) but no test that uses them. Default hyperparameters, 16 chains, whole
-    path gpslc -> sampleITE. The chains differ from the reference's (Philox vs Julia's Xoshiro) and a default run is only 24
-    outer iterations, so the check is distributional: the individuals' mean ITEs must be strongly correlated with the golden
-    means in the typical chain, and for multiplicative_linear every chain must also pass the reference's own gate (at least
-    half of the mean ITEs inside the golden 90 % interval, test/driver.jl:46-52). Measured match rates for all fixtures, and the
-    open question about additive_linear and NEEC at doT = 1, are in DESIGN.md §5 (tools/gpu_golden_probe.py)."""
-    for doT in (0, 1):
-        inside, corr = _golden_match(ctx, name, doT)
-        print(name, doT, "inside: median %.2f min %.2f; corr: median %.2f" % (np.median(inside), inside.min(), np.median(corr)))
-        assert np.median(corr) >= min_corr, (name, doT, np.median(corr))
-        if all_pass_gate:
-            assert inside.min() >= 0.5, (name, doT, inside.min())
+# files the CUDA path reproduces: (name, tag, min gate, min corr, |mean - golden| tolerance, sd ratio range, width ratio range)
+_GOLDEN_PASS = [
+    ("NEEC_sampled", "0.6", 0.95, None, 0.06, (1.6, 2.6), (0.40, 0.70)),          # the reference's own test; measured gate 1.00, mean -0.218 vs -0.209
+    ("NEEC_sampled", "0", 0.85, None, 0.60, (2.0, 3.3), (1.8, 2.8)),              # gate 1.00, mean +0.68 vs +0.29 (wide intervals on both sides)
+    ("multiplicative_linear", "0", 0.95, 0.95, 0.05, (0.95, 1.10), (0.68, 0.86)),   # gate 1.00, corr +0.99, mean -0.848 vs -0.849, sd 2.10 vs 2.04
+    ("multiplicative_linear", "1", 0.95, 0.95, 0.25, (0.90, 1.03), (0.74, 0.92)),   # gate 1.00, corr +0.98, mean -0.20 vs -0.40
+    ("IHDP_sampled", "true", 0.95, 0.97, 0.15, (1.00, 1.14), (0.62, 0.80)),         # binary T: gate 1.00, corr +0.99, mean +2.47 vs +2.39
+    ("IHDP_sampled", "false", 0.95, 0.97, 0.05, (0.98, 1.10), (0.60, 0.77)),        # gate 1.00, corr +0.99, mean -1.329 vs -1.322
+]
+# files it does NOT reproduce, with the measured status (gate, corr) - unexplained without a run of the reference
+_GOLDEN_GAP = [
+    ("NEEC_sampled", "1", 0.00, -0.21), ("NEEC_sampled", "1.0", 0.00, -0.21),
+    ("additive_linear", "0", 0.06, -0.75), ("additive_linear", "1", 0.08, -0.72),
+    ("additive_nonlinear", "0", 0.12, +0.83), ("additive_nonlinear", "1", 0.11, +0.91),
+    ("multiplicative_nonlinear", "0", 0.48, +0.88), ("multiplicative_nonlinear", "1", 0.20, +0.71),
+]
 
 
-@pytest.mark.xfail(reason="open parity question (DESIGN.md §5): with the kernel convention of the reference's current source the mean "
-                          "ITEs of additive_linear come out anti-correlated with the untested golden file", strict=False)
-def test_synthetic_golden_additive_linear(ctx):
-    inside, corr = _golden_match(ctx, "additive_linear", 0)
-    assert np.median(corr) >= 0.5
+@pytest.mark.parametrize("name,tag,min_gate,min_corr,mean_tol,sd_ratio,width_ratio", _GOLDEN_PASS, ids=[f"{a}_{b}" for a, b, *_ in _GOLDEN_PASS])
+def test_reference_golden_file(ctx, name, tag, min_gate, min_corr, mean_tol, sd_ratio, width_ratio):
+    st = _golden_stats(ctx, name, tag)
+    print(name, tag, st)
+    assert st["gate"] >= min_gate, st
+    if min_corr is not None:
+        assert st["corr"] >= min_corr, st
+    assert abs(st["mean"] - st["g_mean"]) <= mean_tol, st
+    assert sd_ratio[0] <= st["sd"] / st["g_sd"] <= sd_ratio[1], st
+    assert width_ratio[0] <= st["width"] / st["g_width"] <= width_ratio[1], st
+
+
+@pytest.mark.parametrize("name,tag,gate,corr", _GOLDEN_GAP, ids=[f"{a}_{b}" for a, b, *_ in _GOLDEN_GAP])
+def test_reference_golden_file_known_gap(ctx, request, name, tag, gate, corr):
+    """Golden files no reference test uses and the CUDA path does not reproduce under ANY of the eight convention combinations of
+    profiles/golden_table_r02.md. Two assertions: (i) the mismatch is the recorded one (a silent change in either direction fails the
+    test); (ii) the reference's gate itself, as a strict expected failure carrying the measured numbers."""
+    st = _golden_stats(ctx, name, tag)
+    print(name, tag, st)
+    assert abs(st["gate"] - gate) <= 0.25 and abs(st["corr"] - corr) <= 0.15, (st, gate, corr)
+    request.applymarker(pytest.mark.xfail(strict=True, reason=f"open parity gap: {100 * gate:.0f} % of 64 chains pass the reference's gate on {name}_{tag}.csv "
+                                                               f"(median correlation with the golden means {corr:+.2f}); same under ess_rule 0/1, l / l^2 and 4x "
+                                                               "budget (profiles/golden_table_r02.md)"))
+    assert st["gate"] >= 0.9, st
 
 
 def test_gpslc_accepts_the_four_csv_shapes(ctx):
@@ -501,8 +682,13 @@ def test_predict_counterfactual_effects(ctx):
     gobj = g.gpslc(counts, X, T, Y, hyperparams=h, ctx=ctx)
     ite, rng_ = g.predictCounterfactualEffects(gobj, 3, fidelity=4, ctx=ctx)
     assert ite.shape == (5, 40, 4 * 3) and rng_[0] == T.min() and rng_[-1] == T.max()
-    M0 = g.ITEDistributions(gobj, rng_[2], ctx=ctx)[0]
-    assert np.all(np.isfinite(ite)) and np.abs(ite[2].mean(axis=1) - M0.mean(axis=0)).max() < 5.0
+    # row d of the sweep is sampleITE at doT_d: same posterior samples, so the per-individual average of the draws must sit at the
+    # mixture mean of the MeanITEs within a few standard errors of the CovITE diagonal (12 draws per individual)
+    M0, C0 = g.ITEDistributions(gobj, rng_[2], ctx=ctx)
+    se = np.sqrt(np.einsum("rii->ri", C0).mean(axis=0) / 12 + M0.var(axis=0) / 12)
+    assert np.all(np.isfinite(ite)) and np.all(np.abs(ite[2].mean(axis=1) - M0.mean(axis=0)) < 6 * se + 1e-6)
+    one = g.sampleITE(gobj, rng_[2], samplesPerPosterior=3, ctx=ctx)
+    assert one.shape == ite[2].shape and np.allclose(one.mean(axis=1), ite[2].mean(axis=1), atol=8 * se.max())
 
 
 def test_counterfactual_sweep_shards_concatenate(ctx):
@@ -519,9 +705,9 @@ def test_counterfactual_sweep_shards_concatenate(ctx):
 
 
 def test_binary_treatment_end_to_end_ihdp(ctx):
-    """IHDP_sampled.csv (n=272, 6 covariates, 200 objects, Bool T): gpslc -> sampleITE(true/false) runs the binary-T
-    sampler; the golden files test/test_results/IHDP_sampled_{true,false}.csv have no test in the reference,
-    so only a loose sanity gate is applied: a majority of mean ITEs inside the golden 90% interval widened by its own width."""
+    """IHDP_sampled.csv (n=272, 6 covariates, 200 objects, Bool T): gpslc -> sampleITE(true/false) -> summarizeEstimates through the
+    public API runs the binary-T sampler (logitT slices); ONE default chain must pass the reference's own gate against the golden
+    files test/test_results/IHDP_sampled_{true,false}.csv (>= 50 % of the mean ITEs inside the golden 90 % interval; measured 0.99)."""
     import pandas as pd
     gobj = g.gpslc(os.path.join(GOLD, "data", "IHDP_sampled.csv"), seed=7, ctx=ctx)
     assert gobj.T.dtype == np.bool_ and len(gobj.posteriorSamples) == 24
@@ -531,8 +717,8 @@ def test_binary_treatment_end_to_end_ihdp(ctx):
         ite = g.sampleITE(gobj, doT, ctx=ctx)
         assert ite.shape == (272, 150) and np.all(np.isfinite(ite))
         exp = pd.read_csv(os.path.join(GOLD, "results", f"IHDP_sampled_{name}.csv"))
-        act = g.summarizeEstimates(ite)
-        wdt = (exp["UpperBound"] - exp["LowerBound"])
-        inside = ((exp["LowerBound"] - wdt <= act["Mean"]) & (act["Mean"] <= exp["UpperBound"] + wdt)).mean()
-        print("IHDP", name, "fraction inside widened golden interval:", inside)
-        assert inside >= 0.5
+        act = g.summarizeEstimates(ite, ctx=ctx)
+        inside = ((exp["LowerBound"] <= act["Mean"]) & (act["Mean"] <= exp["UpperBound"])).mean()
+        print("IHDP", name, "fraction inside the golden interval:", inside)
+        assert inside >= 0.9
+        assert np.corrcoef(act["Mean"], exp["Mean"])[0, 1] >= 0.97
