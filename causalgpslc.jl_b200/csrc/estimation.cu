@@ -465,16 +465,104 @@ __global__ void __launch_bounds__(256) summarize_kernel(const double* __restrict
     }
 }
 
+// Large sample counts (m > 8192: e.g. the draws of all 512 chains pooled, 512 x 150 = 76800 per individual) do not fit a shared-memory
+// sort. The same three statistics by radix selection instead: one CTA per group of 4 adjacent individuals (one 32-byte sector per
+// sample), eight passes over the samples, one per 8-bit digit of the order-preserving 64-bit key, most significant first; every pass
+// builds the digit histograms of all 16 (individual, order statistic) selections at once among the samples that match the selection's
+// prefix so far. The two quantiles need the order statistics l and l+1 each (type 7). HBM-bound: 8 reads of the samples.
+__device__ __forceinline__ unsigned long long f64_key(double x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_f64(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+__global__ void __launch_bounds__(256) summarize_select_kernel(const double* __restrict__ samples, int m, int n, double lowerQ, double upperQ,
+                                                               double* __restrict__ out) {
+    __shared__ unsigned int hist[16][256];
+    __shared__ unsigned long long prefix[16];
+    __shared__ unsigned int rank[16];
+    __shared__ double red[8][4];
+    const int b = blockIdx.y, i0 = blockIdx.x * 4;
+    const int ni = min(4, n - i0);
+    const double* src = samples + (size_t)b * m * n + i0;
+    const int tid = threadIdx.x;
+    if (tid < 16) {
+        const int which = tid & 3;                      // order statistic: lower l, lower l+1, upper l, upper l+1
+        const double h = (m - 1) * ((which < 2) ? lowerQ : upperQ);
+        int l = (int)floor(h);
+        l = max(0, min(l, m - 1));
+        rank[tid] = (unsigned)((which & 1) ? min(l + 1, m - 1) : l);
+        prefix[tid] = 0ull;
+    }
+    // mean
+    double sum[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int s = tid; s < m; s += blockDim.x)
+        for (int k = 0; k < ni; k++) sum[k] += src[(size_t)s * n + k];
+    for (int k = 0; k < 4; k++) {
+        double v = sum[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0) red[tid >> 5][k] = v;
+    }
+    __syncthreads();
+    for (int pass = 0; pass < 8; pass++) {
+        const int shift = 56 - 8 * pass;
+        for (int e = tid; e < 16 * 256; e += blockDim.x) (&hist[0][0])[e] = 0u;
+        __syncthreads();
+        for (int s = tid; s < m; s += blockDim.x) {
+            for (int k = 0; k < ni; k++) {
+                const unsigned long long key = f64_key(src[(size_t)s * n + k]);
+                const unsigned int digit = (unsigned int)(key >> shift) & 255u;
+                const unsigned long long hi = (pass == 0) ? 0ull : (key >> (shift + 8));
+#pragma unroll
+                for (int w = 0; w < 4; w++)
+                    if (pass == 0 || hi == prefix[k * 4 + w]) atomicAdd(&hist[k * 4 + w][digit], 1u);
+            }
+        }
+        __syncthreads();
+        if (tid < 16 && (tid >> 2) < ni) {
+            unsigned int r = rank[tid], d = 0;
+            while (d < 255u && r >= hist[tid][d]) { r -= hist[tid][d]; d++; }
+            rank[tid] = r;
+            prefix[tid] = (prefix[tid] << 8) | d;
+        }
+        __syncthreads();
+    }
+    if (tid < ni) {
+        double* o3 = out + ((size_t)b * n + i0 + tid) * 3;
+        double tot = 0.0;
+        for (int wv = 0; wv < 8; wv++) tot += red[wv][tid];
+        o3[0] = tot / m;
+        const double qs[2] = {lowerQ, upperQ};
+        for (int qi = 0; qi < 2; qi++) {
+            const double h = (m - 1) * qs[qi];
+            int l = (int)floor(h);
+            l = max(0, min(l, m - 1));
+            const double xl = key_f64(prefix[tid * 4 + 2 * qi]), xu = key_f64(prefix[tid * 4 + 2 * qi + 1]);
+            o3[1 + qi] = xl + (h - l) * (xu - xl);
+        }
+    }
+}
+
 int launch_summarize(Ctx* ctx, const double* samples, int batch, int m, int n, double ci, double* out) {
     int mpad = 2;
     while (mpad < m) mpad <<= 1;
-    if (mpad > 8192) return ctx->fail(GPSLC_ERR_UNSUPPORTED, "gpslc_summarize: more than 8192 samples per individual");
+    const double lowerQ = (1.0 - ci) / 2.0, upperQ = 1.0 - lowerQ;
+    if (mpad > 8192) {
+        dim3 grid(ceil_div(n, 4), batch);
+        summarize_select_kernel<<<grid, 256, 0, ctx->stream>>>(samples, m, n, lowerQ, upperQ, out);
+        ctx->launches++;
+        GP_CUDA(ctx, cudaGetLastError());
+        return GPSLC_OK;
+    }
     int IT = (int)((192 * 1024) / ((size_t)mpad * sizeof(double)));
     if (IT > 32) IT = 32;
     if (IT > n) IT = n;
     const size_t smem = (size_t)IT * mpad * sizeof(double);
     GP_CUDA(ctx, cudaFuncSetAttribute(summarize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const double lowerQ = (1.0 - ci) / 2.0, upperQ = 1.0 - lowerQ;
     dim3 grid(ceil_div(n, IT), batch);
     summarize_kernel<<<grid, 256, smem, ctx->stream>>>(samples, m, mpad, n, IT, lowerQ, upperQ, out);
     ctx->launches++;

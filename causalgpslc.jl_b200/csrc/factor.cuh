@@ -557,8 +557,12 @@ __device__ __noinline__ void row_tile_kloop_fold(double* __restrict__ accio, con
 //   void quad(int r0, int r1, int c, double& v00, double& v01, double& v10, double& v11) const
 //        -> K[r0][c], K[r0][c+1], K[r1][c], K[r1][c+1]   (lower triangle / rectangular rows; c even)
 //   double rhs(int which, int r) const
+// GPSLC_FOLD = 1 folds the diagonal tile's k-loop into the k-loop of the panel's first row tile (row_tile_kloop_fold: same B slabs,
+// one pass less over them). Measured on B200 (profiles/fold_ab_r02.md): bit-identical chains, but 3 % SLOWER at c3 (1277 vs 1314
+// sweeps/s), 13 % slower at c2 and 2.5 % at c4 - the folded loop issues one LDS per DMMA (the diagonal operands are not shared
+// between tiles of a warp) and gives up the two-slab stages of the stand-alone diagonal loop. Kept as a build-time experiment, off.
 #ifndef GPSLC_FOLD
-#define GPSLC_FOLD 1    // 0: development A/B switch, separate diagonal k-loop everywhere
+#define GPSLC_FOLD 0
 #endif
 template <class Gen, int TEAM = 0, bool SNAP = false, bool FOLD = (GPSLC_FOLD != 0) && !SNAP>
 __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const int nrhs, double* scratch,

@@ -15,7 +15,12 @@ int ensure_workspace(Ctx* ctx, int NRB, int NCB, long long tasks, int* grid_out,
     // second wave is nearly empty and every task runs at half speed; n = 2048, 64 chains: two CTAs 0.75, one 0.73; n = 4096, 64
     // chains: two 0.81, one 0.83). GPSLC_CTAS_PER_SM overrides (development knob).
     const char* e = getenv("GPSLC_CTAS_PER_SM");
-    int per = (e && atoi(e) > 0) ? atoi(e) : ((team == 1 && ((NCB >= 32 && tasks <= 3LL * ctx->num_sms) || (NCB >= 64 && tasks <= 6LL * ctx->num_sms))) ? 1 : 2);
+    // Cluster teams on large matrices (measured, 32 augmented 16384 x 16384 factorizations of the n = 8192 counterfactual sweep:
+    // teams of 8 with two CTAs per SM 2.3 s, teams of 4 with one CTA per SM 1.7 s): 256 CTAs on 148 SMs leave every team waiting for its
+    // members that share an SM, so large-matrix teams get an SM per CTA.
+    int per = (e && atoi(e) > 0) ? atoi(e)
+              : ((team == 1 && ((NCB >= 32 && tasks <= 3LL * ctx->num_sms) || (NCB >= 64 && tasks <= 6LL * ctx->num_sms))) ? 1
+                 : (team > 1 && NCB >= 32) ? 1 : 2);
     if (per > 2) per = 2;
     // team > 1: one L scratch per team (cluster), one z buffer per CTA; *grid_out is the number of teams
     const long long max_slots = (long long)per * ctx->num_sms / team;
@@ -54,7 +59,8 @@ int ensure_workspace(Ctx* ctx, int NRB, int NCB, long long tasks, int* grid_out,
 // The redundant diagonal work of a team is about 1.7 * team / NCB of the total. GPSLC_TEAM overrides (development knob).
 int pick_team(Ctx* ctx, long long tasks, int NCB) {
     if (const char* e = getenv("GPSLC_TEAM")) { const int g = atoi(e); if (g == 1 || g == 2 || g == 4 || g == 8) return g; }
-    const long long resident = 2LL * ctx->num_sms;
+    // large matrices (>= 32 panels): one CTA per SM (see ensure_workspace), so the team size is chosen against the SM count
+    const long long resident = (NCB >= 32 ? 1LL : 2LL) * ctx->num_sms;
     int g = 1;
     if (NCB < 8) return 1;   // below n = 512 the redundant diagonal work and the cluster barriers eat the gain
     while (g < 8 && tasks * (2 * g) <= resident && 2 * g <= NCB) g *= 2;   // SMs would idle otherwise: larger teams win even at

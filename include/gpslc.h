@@ -225,7 +225,8 @@ int gpslc_ite_summary(gpslc_ctx* ctx, int loc, const gpslc_data* data, const dou
  *                            m = R*spp; for one doT and all chains pooled, m = n_chains*R*spp)
  *   out     [batch][n][3]  — Mean, LowerBound, UpperBound
  * With loc = GPSLC_DEVICE a counterfactual sweep is summarised where gpslc_ite left it in HBM (BASELINE config c5 never
- * ships its 168 MB of draws to the host). m <= 8192. */
+ * ships its 168 MB of draws to the host). Any m: up to 8192 samples per individual are sorted in shared memory, more (e.g. the draws
+ * of all chains pooled) go through a radix selection of the four order statistics. */
 int gpslc_summarize(gpslc_ctx* ctx, int loc, const double* samples, int batch, int m, int n, double credible_interval,
                     double* out);
 

@@ -557,8 +557,17 @@ def test_summarize_estimates_on_device(ctx, kats):
             mean, lb, ub = oe.summarize_estimates(x[b].T, 0.9)
             assert np.allclose(got[b, :, 0], mean, rtol=1e-12, atol=1e-13)
             assert np.allclose(got[b, :, 1], lb, rtol=1e-12, atol=1e-13) and np.allclose(got[b, :, 2], ub, rtol=1e-12, atol=1e-13)
-    with pytest.raises(Exception):
-        ge.summarize(np.zeros((1, 9000, 2)), 0.9, ctx=ctx)      # more than 8192 samples per individual: refused loudly
+    # more than 8192 samples per individual (pooled chains): radix-selection path; ties, negative values, ragged n, both quantiles
+    for batch, m, n in ((1, 9000, 2), (2, 20000, 7), (1, 76800, 9)):
+        x = rng.standard_normal((batch, m, n)) * 3 + 1
+        x[:, ::7, :] = np.round(x[:, ::7, :], 1)                # many exact ties
+        for ci in (0.9, 0.5):
+            got = ge.summarize(x, ci, ctx=ctx)
+            for b in range(batch):
+                mean, lb, ub = oe.summarize_estimates(x[b].T, ci)
+                assert np.allclose(got[b, :, 0], mean, rtol=1e-11, atol=1e-12)
+                assert np.array_equal(got[b, :, 1], lb) or np.allclose(got[b, :, 1], lb, rtol=1e-13, atol=1e-14)
+                assert np.allclose(got[b, :, 2], ub, rtol=1e-13, atol=1e-14)
 
 
 # ------------------------------------------------------------------------------------------------ public API end to end
