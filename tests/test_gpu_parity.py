@@ -669,6 +669,28 @@ def test_reference_golden_file_known_gap(ctx, request, name, tag, gate, corr):
     assert st["gate"] >= 0.9, st
 
 
+def test_data_prep_and_persistence_round_trip_through_the_gpu_path(ctx, tmp_path):
+    """SURVEY section 8 row f4, the formats either side of the hot path: prepareData (rows sorted by obj, SigmaU from the object
+    counts, src/data.jl:20-70) feeds the sampler, and a saved / re-loaded GPSLCObject (src/io.jl; test/io.jl) drives the estimation
+    kernels to exactly the same draws as the object it was saved from."""
+    path = os.path.join(GOLD, "data", "minimal.csv")
+    SigmaU, obj, X, T, Y = g.prepareData(path)
+    assert list(obj) == sorted(obj) and SigmaU.shape == (24, 24) and X.shape == (24, 2)
+    h = g.getHyperParameters(); h.nOuter, h.nBurnIn = 6, 3
+    a = g.gpslc(path, hyperparams=h, seed=11, ctx=ctx)
+    # the same data handed over as (SigmaU-structure, X, T, Y): identical chain
+    b = g.gpslc(g.objectCounts(obj), X, T, Y, hyperparams=g.HyperParameters(1, 6, 10, 5, 3, 1, 1e-10), seed=11, ctx=ctx)
+    assert np.array_equal(a.posteriorPacked, b.posteriorPacked)
+    g.saveGPSLCObject(a, str(tmp_path / "run.gpslc"))
+    back = g.loadGPSLCObject(str(tmp_path / "run"))
+    assert np.array_equal(back.posteriorPacked, a.posteriorPacked) and back.hyperparams == a.hyperparams
+    assert np.array_equal(back.priorparams["SigmaU"], SigmaU)
+    assert np.array_equal(g.sampleITE(back, 0.4, ctx=ctx), g.sampleITE(a, 0.4, ctx=ctx))
+    assert np.array_equal(g.sampleSATE(back, 0.4, ctx=ctx), g.sampleSATE(a, 0.4, ctx=ctx))
+    u1 = g.extractParameters(back, 4); u2 = g.extractParameters(a, 4)
+    assert all(np.array_equal(x, y) for x, y in zip(u1, u2))
+
+
 def test_gpslc_accepts_the_four_csv_shapes(ctx):
     """test/gpslc.jl: full / no covariates / no objects / neither, with nOuter=5, nMHInner=1, nESInner=1."""
     for f, has_u, has_x in (("minimal.csv", True, True), ("no_cov.csv", True, False), ("no_objects.csv", False, True),
