@@ -74,6 +74,11 @@ int pick_team(Ctx* ctx, long long tasks, int NCB) {
 // 1x4 strip of a column block so that stores are 32-byte vectors along the fastest (row) dimension.
 // feat: [batch or 1][D][n] feature columns (row-contiguous), w: [batch][D] = 1 / lengthscale, scale/noise: [batch].
 // X2 != X1 is supported (likelihood.jl:27 builds K(T, doT)).
+// one aligned 32-byte sector per lane: 256-bit streaming store (STG.E.EF.256 on sm_100)
+__device__ __forceinline__ void store4_cs(double* dst, double a, double b, double c, double d) {
+    asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
 __global__ void __launch_bounds__(256) cov_build_kernel(int n, int D, const double* __restrict__ f1, const double* __restrict__ f2,
                                                         size_t feat_stride, const double* __restrict__ w,
                                                         const double* __restrict__ scale, const double* __restrict__ noise,
@@ -135,9 +140,7 @@ __global__ void __launch_bounds__(256) cov_build_kernel(int n, int D, const doub
         const int r = r0 + tr;
         double* dst = Kb + (size_t)c * n + r;
         if (r + 3 < n && ((((size_t)c * n + r) & 3) == 0) && ((reinterpret_cast<uintptr_t>(Kb) & 31) == 0)) {
-            // 32-byte vector store
-            double4 v4 = make_double4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<double4*>(dst) = v4;
+            store4_cs(dst, v[0], v[1], v[2], v[3]);
         } else {
 #pragma unroll
             for (int i = 0; i < 4; i++)
@@ -147,20 +150,19 @@ __global__ void __launch_bounds__(256) cov_build_kernel(int n, int D, const doub
 }
 
 // K(X, X): the matrix is symmetric, so only the 64 x 64 tiles on and below the block diagonal are computed (half the FP64 work:
-// at D ~ 12 an entry costs 2 D + 12 FP64-pipe instructions, which is what keeps a one-sided kernel off the HBM roofline) and every
-// off-diagonal tile is written twice, as it is and transposed. Both stores come straight from the 4 x 4 register block of a thread
-// as 32-byte sector-aligned pieces (streaming stores, evict-first): the direct store is contiguous along a column, the transposed
-// one writes one full sector per (thread, row) — L2 assembles the lines, no shared-memory transpose, no barrier after the feature
-// staging, 12.5 KB of shared memory and <= 64 registers, so four CTAs are resident per SM. K comes out exactly symmetric.
-__device__ __forceinline__ void store4_cs(double* dst, const double (&v)[4]) {
-    __stcs(reinterpret_cast<double2*>(dst), make_double2(v[0], v[1]));
-    __stcs(reinterpret_cast<double2*>(dst) + 1, make_double2(v[2], v[3]));
-}
-
+// at D ~ 12 an entry costs 2 D + 12 FP64-pipe instructions, and the FP64 pipe is the second roof of this kernel) and every
+// off-diagonal tile is written twice, as it is and transposed, straight from the 4 x 4 register block of a thread with 256-bit
+// streaming stores (STG.E.EF.256, sm_100): every store instruction writes one full, aligned 32-byte sector per lane, so L2 never sees
+// a partial sector - ncu on the first version of this kernel, which wrote each sector as two 128-bit halves, showed the L1/LSU pipe
+// at 94 % and L2 at 66 % with DRAM at 36-50 % (profiles/ncu_cov_build_r02.md). The direct store is contiguous along a column
+// (16 lanes x 32 B), the transposed one scatters full sectors that L2 assembles into lines. No shared-memory transpose, no barrier
+// after the feature staging, 12.5 KB of shared memory and 64 registers: four CTAs per SM. Feature rows are staged permuted
+// (row r at (r & 3) * 16 + (r >> 2)) so that the four row values of a thread come from four conflict-free LDS.64.
+// K comes out exactly symmetric.
 __global__ void __launch_bounds__(256, 4) cov_build_sym_kernel(int n, int D, const double* __restrict__ f, size_t feat_stride,
                                                                const double* __restrict__ w, const double* __restrict__ scale,
                                                                const double* __restrict__ noise, int has_noise, double* __restrict__ K) {
-    extern __shared__ __align__(16) double sh[];  // [32] 2^(i/32) table, [D][64] column features, [D][64] row features
+    extern __shared__ __align__(16) double sh[];  // [32] 2^(i/32) table, [D][64] column features, [D][64] row features (permuted)
     const int b = blockIdx.z;
     // linear index of a lower-triangular tile pair -> (bi >= bj)
     const int p = blockIdx.x;
@@ -176,14 +178,16 @@ __global__ void __launch_bounds__(256, 4) cov_build_sym_kernel(int n, int D, con
     if (threadIdx.x < 32) tab[threadIdx.x] = GPSLC_EXP2_TAB[threadIdx.x];
     for (int i = threadIdx.x; i < D * 64; i += blockDim.x) {
         const int d = i >> 6, o = i & 63;
+        const int po = d * 64 + (o & 3) * 16 + (o >> 2);      // permuted position inside the dimension's 64 values
         const double sw = w[(size_t)b * D + d];     // 1 / lengthscale
-        sc[i] = (c0 + o < n) ? pf[(size_t)d * n + c0 + o] * sw : 0.0;
-        sr[i] = (r0 + o < n) ? pf[(size_t)d * n + r0 + o] * sw : 0.0;
+        sc[po] = (c0 + o < n) ? pf[(size_t)d * n + c0 + o] * sw : 0.0;
+        sr[po] = (r0 + o < n) ? pf[(size_t)d * n + r0 + o] * sw : 0.0;
     }
     __syncthreads();
     const double s = scale[b];
     const double nz = has_noise ? noise[b] : 0.0;
-    const int tr = (threadIdx.x & 15) * 4, tc = (threadIdx.x >> 4) * 4;
+    const int lr = threadIdx.x & 15, lc = threadIdx.x >> 4;
+    const int tr = lr * 4, tc = lc * 4;
     double acc[4][4];       // [column j][row i]
 #pragma unroll
     for (int j = 0; j < 4; j++)
@@ -191,9 +195,9 @@ __global__ void __launch_bounds__(256, 4) cov_build_sym_kernel(int n, int D, con
         for (int i = 0; i < 4; i++) acc[j][i] = 0.0;
 #pragma unroll 2
     for (int d = 0; d < D; d++) {
-        const double2 ra = *reinterpret_cast<const double2*>(sr + d * 64 + tr), rb = *reinterpret_cast<const double2*>(sr + d * 64 + tr + 2);
-        const double2 ca = *reinterpret_cast<const double2*>(sc + d * 64 + tc), cb = *reinterpret_cast<const double2*>(sc + d * 64 + tc + 2);
-        const double zr[4] = {ra.x, ra.y, rb.x, rb.y}, zc[4] = {ca.x, ca.y, cb.x, cb.y};
+        double zr[4], zc[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { zr[i] = sr[d * 64 + i * 16 + lr]; zc[i] = sc[d * 64 + i * 16 + lc]; }
 #pragma unroll
         for (int j = 0; j < 4; j++)
 #pragma unroll
@@ -215,7 +219,7 @@ __global__ void __launch_bounds__(256, 4) cov_build_sym_kernel(int n, int D, con
         const int c = c0 + tc + j, r = r0 + tr;
         if (c >= n) continue;
         double* dst = Kb + (size_t)c * n + r;
-        if (vec_ok && r + 3 < n) store4_cs(dst, acc[j]);
+        if (vec_ok && r + 3 < n) store4_cs(dst, acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
         else {
 #pragma unroll
             for (int i = 0; i < 4; i++)
@@ -228,13 +232,12 @@ __global__ void __launch_bounds__(256, 4) cov_build_sym_kernel(int n, int D, con
     for (int i = 0; i < 4; i++) {
         const int cc = r0 + tr + i, rr = c0 + tc;
         if (cc >= n) continue;
-        const double v[4] = {acc[0][i], acc[1][i], acc[2][i], acc[3][i]};
         double* dst = Kb + (size_t)cc * n + rr;
-        if (vec_ok && rr + 3 < n) store4_cs(dst, v);
+        if (vec_ok && rr + 3 < n) store4_cs(dst, acc[0][i], acc[1][i], acc[2][i], acc[3][i]);
         else {
 #pragma unroll
             for (int jj = 0; jj < 4; jj++)
-                if (rr + jj < n) dst[jj] = v[jj];
+                if (rr + jj < n) dst[jj] = acc[jj][i];
         }
     }
 }
