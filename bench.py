@@ -293,6 +293,9 @@ def run_ours(args):
         # of the cluster-team kernels of the slice sampler's tail rounds)
         sw = ChainSampler(pri, X, T, Y, w["nU"], counts, 1, 1, 1, n_chains=C, seed=98, chain_offset=rank * C, ctx=ctx)
         sw.run(1)
+        if world > 1:
+            all_gather_samples_device(sw, world)     # first use of the all_gather channels
+            torch.cuda.synchronize()
         pw = sw.samples()
         sw.close()
         ge.sate(pw, X, T, Y, w["nU"], 0.0, np.zeros(1, dtype=np.int32), 1e-10, spp, seed=98, chain_offset=rank * C, ctx=ctx)

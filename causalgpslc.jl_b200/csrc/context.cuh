@@ -109,7 +109,10 @@ struct ArenaScope {
 // Reserve factor workspaces for `tasks` independent NRB x NCB block matrices and return the grid size to launch: one slot per
 // resident CTA, fewer when there are fewer tasks or when the slots would not fit in free HBM (large n). With team > 1 (cluster
 // launches, factor.cuh) a slot of L scratch serves a whole team and *grid is the number of teams.
-int ensure_workspace(Ctx* ctx, int NRB, int NCB, long long tasks, int* grid, int team = 1);
+int ensure_workspace(Ctx* ctx, int NRB, int NCB, long long tasks, int* grid, int team = 1, int split = 0);
+// split > 0: a slot holds block rows >= split only (shared-prefix factorizations, factor.cuh PRE)
+// z / w side buffers only (one per CTA) for kernels that keep their factor elsewhere; sets ctx->slot_z_d
+int ensure_zbuf(Ctx* ctx, int NCB, long long ctas);
 // cluster size (1, 2, 4 or 8 CTAs per matrix) for a launch with `tasks` independent factorizations of NCB block columns
 int pick_team(Ctx* ctx, long long tasks, int NCB);
 

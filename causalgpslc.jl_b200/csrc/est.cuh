@@ -20,6 +20,14 @@ struct EstArgs {
     int var_as_std;
     int ls_unsquared;               // experiment knob, see sampler.cuh
     int dot0;                       // global index of doT[0] (sharded sweeps): only the draws' RNG streams depend on it
+    // shared-prefix mode (several doT values per posterior sample): chol(Kp) of base task b = chain*R + r was computed once by
+    // ite_base_kernel; this launch covers the base tasks [base0, base0 + base_n) and all doT values
+    int base0, base_n;
+    const double* base_L;           // [base_n][slot_lo] factor scratch of Kp (rows < NCB1)
+    const double* base_linv;        // [base_n][NCB1][LINV_D]
+    const double* base_z;           // [base_n][npad] L11^-1 Y
+    const int* base_info;           // [base_n]
+    size_t slot_lo;
 };
 
 struct Ctx;

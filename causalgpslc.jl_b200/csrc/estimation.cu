@@ -175,7 +175,52 @@ __device__ inline void fill_ite_spec(const EstArgs& a, const double* rec, double
 // one task = (doT d, chain c, retained sample r): augmented Cholesky, MeanITE, optional CovITE, ITE draws.
 // TEAM = 0: one CTA per task, tasks handed out from an atomic counter. TEAM = 1: one thread-block cluster per task (few large
 // tasks, c5 of BASELINE.json); scratch is indexed by cluster, z / xi buffers by CTA, tasks are dealt out round-robin.
+// chol(Kp), L11^-1 Y and the P2 outputs of every panel, once per posterior sample (base task b = chain * R + r): what ite_kernel<.., true>
+// continues from for every doT value. TEAM = 1: one cluster per base task; TEAM = 2: the whole cooperatively launched grid on one base
+// task after the other (few large samples: the n = 8192 sweep has ONE).
 template <int TEAM>
+__global__ void __launch_bounds__(FTHREADS, 2)
+ite_base_kernel(EstArgs a, double* base_L, double* base_linv, double* base_z, int* base_info, double* zbuf, size_t slot_z,
+                unsigned int* counter, unsigned int* gbar) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FactorSmem& sm = *reinterpret_cast<FactorSmem*>(smem_raw);
+    __shared__ IteSpec spec;
+    __shared__ unsigned int job;
+    factor_smem_init(sm);
+    if (threadIdx.x == 0) sm.gbar = gbar;
+    Pipe pipe{0, 0};
+    const int NCB1 = ceil_div(a.n, NB), npad = NCB1 * NB;
+    const int trank = (TEAM == 1) ? (int)cluster_rank() : (TEAM == 2) ? (int)blockIdx.x : 0;
+    const unsigned int team = (TEAM == 1) ? cluster_id_x() : blockIdx.x, nteams = (TEAM == 1) ? cluster_count_x() : gridDim.x;
+    double* my_z = zbuf + (size_t)blockIdx.x * slot_z;
+    for (unsigned int round = 0;; round++) {
+        unsigned int u;
+        if constexpr (TEAM == 2) u = round;
+        else if constexpr (TEAM == 1) u = team + round * nteams;
+        else {
+            if (threadIdx.x == 0) job = atomicAdd(counter, 1u);
+            __syncthreads();
+            u = job;
+        }
+        if (u >= (unsigned)a.base_n) break;
+        const int b = a.base0 + (int)u, r = b % a.R, c = b / a.R;
+        const double* rec = a.samples + ((size_t)a.ret_idx[r] * a.n_chains + c) * a.stride;
+        fill_ite_spec(a, rec, 0.0, &spec);          // Kp does not depend on doT
+        __syncthreads();
+        IteGen gen{&spec, sm.exp2tab};
+        factor_run<IteGen, TEAM, false, false, false>(gen, NCB1, NCB1, 1, base_L + (size_t)u * a.slot_lo, my_z, sm, pipe, 1 << 30, nullptr, 0,
+                                                      nullptr, nullptr, 0, base_linv + (size_t)u * NCB1 * LINV_D);
+        if (trank == 0) {
+            if (threadIdx.x == 0) base_info[u] = sm.out.info;
+            for (int i = threadIdx.x; i < npad; i += blockDim.x) base_z[(size_t)u * npad + i] = my_z[i];
+        }
+        if constexpr (TEAM == 1) cluster_barrier();
+        else if constexpr (TEAM == 2) grid_barrier(gbar);
+        else __syncthreads();
+    }
+}
+
+template <int TEAM, bool PRE = false>
 __global__ void __launch_bounds__(FTHREADS, 2)
 ite_kernel(EstArgs a, double* scratch, size_t slot_scratch, double* zbuf, size_t slot_z, double* xibuf, unsigned int* counter) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -190,7 +235,10 @@ ite_kernel(EstArgs a, double* scratch, size_t slot_scratch, double* zbuf, size_t
     double* my_scratch = scratch + (size_t)team * slot_scratch;
     double* my_z = zbuf + (size_t)blockIdx.x * slot_z;
     double* xi = xibuf + (size_t)blockIdx.x * 4 * a.n;
-    const unsigned int total = (unsigned)a.n_doT * a.n_chains * a.R;
+    const unsigned int nbase = (unsigned)a.n_chains * a.R;
+    const unsigned int total = PRE ? (unsigned)a.n_doT * a.base_n : (unsigned)a.n_doT * nbase;
+    // PRE: the lower-left and lower-right blocks only (block rows >= NCB1) live in this task's scratch
+    const size_t hi_off = PRE ? row_off(NCB1) : 0;
     for (unsigned int round = 0;; round++) {
         unsigned int t;
         if constexpr (TEAM != 0) {
@@ -201,14 +249,23 @@ ite_kernel(EstArgs a, double* scratch, size_t slot_scratch, double* zbuf, size_t
             t = job;
         }
         if (t >= total) break;
+        unsigned int ub = 0;                 // base task inside this launch's chunk (PRE)
+        if constexpr (PRE) { ub = t % a.base_n; t = (t / a.base_n) * nbase + a.base0 + ub; }     // -> global task index d * nbase + b
         const int r = t % a.R, c = (t / a.R) % a.n_chains, d = t / (a.R * a.n_chains);
         const double* rec = a.samples + ((size_t)a.ret_idx[r] * a.n_chains + c) * a.stride;
         fill_ite_spec(a, rec, a.doT[d], &spec);
+        if constexpr (PRE)
+            for (int i = threadIdx.x; i < npad; i += blockDim.x) my_z[i] = a.base_z[(size_t)ub * npad + i];     // L11^-1 Y of the shared factor
         __syncthreads();
         IteGen gen{&spec, sm.exp2tab};
         double* cov = a.cov_out ? a.cov_out + (size_t)t * a.n * a.n : nullptr;
-        factor_run<IteGen, TEAM, true>(gen, NCB, NCB, 1, my_scratch, my_z, sm, pipe, NCB1, cov, a.n);
-        const int info = sm.out.info;
+        if constexpr (PRE)
+            factor_run<IteGen, TEAM, true, false, true>(gen, NCB, NCB, 1, my_scratch, my_z, sm, pipe, NCB1, cov, a.n,
+                                                        a.base_L + (size_t)ub * a.slot_lo, a.base_linv + (size_t)ub * NCB1 * LINV_D, NCB1);
+        else
+            factor_run<IteGen, TEAM, true>(gen, NCB, NCB, 1, my_scratch, my_z, sm, pipe, NCB1, cov, a.n);
+        int info = sm.out.info;
+        if constexpr (PRE) { if (a.base_info[ub] != 0) info = a.base_info[ub]; }
         if (threadIdx.x == 0 && trank == 0 && a.info) a.info[t] = info;
         // MeanITE = -(pre-solve residual of the second block); every CTA of a team holds the same residual in its own zbuf
         const double* wres = my_z + (size_t)MAXRHS * (2 * npad) + npad;
@@ -230,7 +287,7 @@ ite_kernel(EstArgs a, double* scratch, size_t slot_scratch, double* zbuf, size_t
                     double accv[4] = {0.0, 0.0, 0.0, 0.0};
                     const int I = NCB1 + (i >> 6), ri = i & 63;
                     for (int jb = 0; jb <= (i >> 6); jb++) {
-                        const double* blk = my_scratch + block_off(I, NCB1 + jb, NCB);
+                        const double* blk = my_scratch + (block_off(I, NCB1 + jb, NCB) - hi_off);
                         const int jmax = (jb == (i >> 6)) ? ri : 63;
                         for (int jj = 0; jj <= jmax; jj++) {
                             const double l = blk[elem_off(ri, jj)];
@@ -357,42 +414,153 @@ sate_kernel(EstArgs a, double* scratch, size_t slot_scratch, double* zbuf, size_
     }
 }
 
+// launch one of the ite_kernel instantiations on `grid` teams of `team` CTAs
+template <bool PRE>
+static int launch_ite_kernel(Ctx* ctx, const EstArgs& a, int team, int grid, double* xi) {
+    if (team == 1) {
+        GP_CUDA(ctx, cudaFuncSetAttribute(ite_kernel<0, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
+        ite_kernel<0, PRE><<<grid, FTHREADS, sizeof(FactorSmem), ctx->stream>>>(a, ctx->scratch, ctx->slot_scratch_d, ctx->zbuf, ctx->slot_z_d, xi,
+                                                                                ctx->counter);
+        ctx->launches++;
+        GP_CUDA(ctx, cudaGetLastError());
+        return GPSLC_OK;
+    }
+    GP_CUDA(ctx, cudaFuncSetAttribute(ite_kernel<1, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = team; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(FTHREADS); cfg.dynamicSmemBytes = sizeof(FactorSmem); cfg.stream = ctx->stream;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.gridDim = dim3(grid * team);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, ite_kernel<1, PRE>, a, ctx->scratch, ctx->slot_scratch_d, ctx->zbuf, ctx->slot_z_d, xi, ctx->counter);
+    ctx->launches++;
+    if (e != cudaSuccess) return ctx->cuda_fail(e, "ite_kernel");
+    return GPSLC_OK;
+}
+
+// number of teams of `team` CTAs that can be resident for kernel k (clusters), clipped to `grid`
+template <class K>
+static int clip_to_resident_clusters(Ctx* ctx, K k, int team, int grid, int* out) {
+    GP_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = team; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(FTHREADS); cfg.dynamicSmemBytes = sizeof(FactorSmem); cfg.stream = ctx->stream;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.gridDim = dim3(grid * team);
+    int max_clusters = 0;
+    GP_CUDA(ctx, cudaOccupancyMaxActiveClusters(&max_clusters, k, &cfg));
+    if (max_clusters < 1) return ctx->fail(GPSLC_ERR_CUDA, "no resident cluster of the requested size");
+    *out = grid > max_clusters ? max_clusters : grid;
+    return GPSLC_OK;
+}
+
+// Several doT values per posterior sample (predictCounterfactualEffects, src/prediction.jl:23-36): chol(Kp), L11^-1 Y and the panels'
+// P2 outputs are computed ONCE per (chain, retained sample) by ite_base_kernel and every (doT, chain, sample) task continues from
+// them (factor.cuh, PRE): 7 n^3 / 3 flops per doT instead of 8 n^3 / 3. The base tasks are processed in chunks that fit a fraction
+// of the free device memory. GPSLC_ITE_SHARE=0 forces the fused one-Cholesky-per-task path (development knob).
+static int launch_ite_shared(Ctx* ctx, const EstArgs& a0) {
+    EstArgs a = a0;
+    const int NCB1 = ceil_div(a.n, NB), NCB = 2 * NCB1, npad = NCB1 * NB;
+    const long long nbase = (long long)a.n_chains * a.R;
+    const size_t slot_lo = row_off(NCB1);
+    const size_t per_base = (slot_lo + (size_t)NCB1 * LINV_D + npad) * sizeof(double) + sizeof(int);
+    size_t free_b = 0, total_b = 0;
+    GP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    long long chunk = (long long)((double)free_b * 0.25 / (double)per_base);
+    if (chunk < 1) return ctx->fail(GPSLC_ERR_CUDA, "not enough device memory for one shared Kp factor");
+    if (chunk > nbase) chunk = nbase;
+    double *bL = nullptr, *blinv = nullptr, *bz = nullptr; int* binfo = nullptr; unsigned int* gbar = nullptr;
+    GP_CUDA(ctx, ctx->arena_alloc(reinterpret_cast<void**>(&bL), (size_t)chunk * slot_lo * sizeof(double)));
+    GP_CUDA(ctx, ctx->arena_alloc(reinterpret_cast<void**>(&blinv), (size_t)chunk * NCB1 * LINV_D * sizeof(double)));
+    GP_CUDA(ctx, ctx->arena_alloc(reinterpret_cast<void**>(&bz), (size_t)chunk * npad * sizeof(double)));
+    GP_CUDA(ctx, ctx->arena_alloc(reinterpret_cast<void**>(&binfo), (size_t)chunk * sizeof(int)));
+    GP_CUDA(ctx, ctx->arena_alloc(reinterpret_cast<void**>(&gbar), 2 * sizeof(unsigned int)));
+    double* xi = nullptr;
+    size_t xi_cap = 0;
+    for (long long b0 = 0; b0 < nbase; b0 += chunk) {
+        const int nb = (int)((nbase - b0 < chunk) ? nbase - b0 : chunk);
+        a.base0 = (int)b0; a.base_n = nb; a.base_L = bL; a.base_linv = blinv; a.base_z = bz; a.base_info = binfo; a.slot_lo = slot_lo;
+        // ---- phase A: the shared factors of this chunk (they go to bL; only the per-CTA z buffers of the context are used)
+        {
+            const int gmax = ctx->num_sms < NCB1 ? ctx->num_sms : NCB1;        // grid mode: at most one CTA per block row, one per SM
+            if ((long long)nb * 16 <= gmax) {
+                // few large samples (the n = 8192 sweep has ONE): the whole cooperatively launched grid factors one Kp after the other
+                GP_TRY(ensure_zbuf(ctx, NCB1, gmax));
+                GP_CUDA(ctx, cudaMemsetAsync(gbar, 0, 2 * sizeof(unsigned int), ctx->stream));
+                GP_CUDA(ctx, cudaFuncSetAttribute(ite_base_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
+                void* args[] = {(void*)&a, (void*)&bL, (void*)&blinv, (void*)&bz, (void*)&binfo, (void*)&ctx->zbuf, (void*)&ctx->slot_z_d,
+                                (void*)&ctx->counter, (void*)&gbar};
+                cudaError_t e = cudaLaunchCooperativeKernel((void*)ite_base_kernel<2>, dim3(gmax), dim3(FTHREADS), args, sizeof(FactorSmem), ctx->stream);
+                ctx->launches++;
+                if (e != cudaSuccess) return ctx->cuda_fail(e, "ite_base_kernel (cooperative)");
+            } else {
+                const int team = pick_team(ctx, nb, NCB1);
+                const int per = (team > 1 && NCB1 >= 32) ? 1 : 2;
+                long long grid = (long long)per * ctx->num_sms / team;
+                if (grid > nb) grid = nb;
+                int g = (int)grid;
+                if (team > 1) GP_TRY(clip_to_resident_clusters(ctx, ite_base_kernel<1>, team, g, &g));
+                GP_TRY(ensure_zbuf(ctx, NCB1, (long long)g * team));
+                GP_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, sizeof(unsigned int), ctx->stream));
+                if (team > 1) {
+                    cudaLaunchConfig_t cfg = {};
+                    cudaLaunchAttribute attr[1];
+                    attr[0].id = cudaLaunchAttributeClusterDimension;
+                    attr[0].val.clusterDim.x = team; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                    cfg.blockDim = dim3(FTHREADS); cfg.dynamicSmemBytes = sizeof(FactorSmem); cfg.stream = ctx->stream;
+                    cfg.attrs = attr; cfg.numAttrs = 1;
+                    cfg.gridDim = dim3(g * team);
+                    cudaError_t e = cudaLaunchKernelEx(&cfg, ite_base_kernel<1>, a, bL, blinv, bz, binfo, ctx->zbuf, ctx->slot_z_d, ctx->counter, gbar);
+                    ctx->launches++;
+                    if (e != cudaSuccess) return ctx->cuda_fail(e, "ite_base_kernel");
+                } else {
+                    GP_CUDA(ctx, cudaFuncSetAttribute(ite_base_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
+                    ite_base_kernel<0><<<g, FTHREADS, sizeof(FactorSmem), ctx->stream>>>(a, bL, blinv, bz, binfo, ctx->zbuf, ctx->slot_z_d, ctx->counter, gbar);
+                    ctx->launches++;
+                    GP_CUDA(ctx, cudaGetLastError());
+                }
+            }
+        }
+        // ---- phase B: every (doT, base task) of the chunk continues from its shared factor
+        {
+            const long long total = (long long)a.n_doT * nb;
+            int team = pick_team(ctx, total, NCB);
+            int grid = 0;
+            GP_TRY(ensure_workspace(ctx, NCB, NCB, total, &grid, team, NCB1));
+            if (team > 1) GP_TRY(clip_to_resident_clusters(ctx, ite_kernel<1, true>, team, grid, &grid));
+            GP_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, sizeof(unsigned int), ctx->stream));
+            const size_t need_xi = (size_t)grid * team * 4 * a.n * sizeof(double);
+            if (need_xi > xi_cap) { GP_CUDA(ctx, ctx->arena_alloc(reinterpret_cast<void**>(&xi), need_xi)); xi_cap = need_xi; }
+            GP_TRY(launch_ite_kernel<true>(ctx, a, team, grid, xi));
+        }
+    }
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    if (e2 != cudaSuccess) return ctx->cuda_fail(e2, "ite_kernel (shared Kp)");
+    return GPSLC_OK;
+}
+
 int launch_ite(Ctx* ctx, const EstArgs& a) {
     const int NCB = 2 * ceil_div(a.n, NB);
     const long long total = (long long)a.n_doT * a.n_chains * a.R;
     if (total == 0) return GPSLC_OK;
+    {
+        const char* e = getenv("GPSLC_ITE_SHARE");
+        const bool share = e ? (atoi(e) != 0) : true;
+        if (share && a.n_doT >= 2) return launch_ite_shared(ctx, a);
+    }
     int team = pick_team(ctx, total, NCB);
     int grid = 0;   // number of scratch slots == number of teams
     GP_TRY(ensure_workspace(ctx, NCB, NCB, total, &grid, team));
+    if (team > 1) GP_TRY(clip_to_resident_clusters(ctx, ite_kernel<1, false>, team, grid, &grid));
     GP_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, sizeof(unsigned int), ctx->stream));
     double* xi = nullptr;
-    cudaError_t e = cudaSuccess;
-    if (team == 1) {
-        GP_CUDA(ctx, cudaFuncSetAttribute(ite_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
-        GP_CUDA(ctx, ctx->arena_alloc(reinterpret_cast<void**>(&xi), (size_t)grid * 4 * a.n * sizeof(double)));
-        ite_kernel<0><<<grid, FTHREADS, sizeof(FactorSmem), ctx->stream>>>(a, ctx->scratch, ctx->slot_scratch_d, ctx->zbuf, ctx->slot_z_d, xi,
-                                                                         ctx->counter);
-        e = cudaGetLastError();
-    } else {
-        GP_CUDA(ctx, cudaFuncSetAttribute(ite_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
-        cudaLaunchConfig_t cfg = {};
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = team; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.blockDim = dim3(FTHREADS); cfg.dynamicSmemBytes = sizeof(FactorSmem); cfg.stream = ctx->stream;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        cfg.gridDim = dim3(grid * team);
-        int max_clusters = 0;
-        GP_CUDA(ctx, cudaOccupancyMaxActiveClusters(&max_clusters, ite_kernel<1>, &cfg));
-        if (max_clusters < 1) return ctx->fail(GPSLC_ERR_CUDA, "ite_kernel: no resident cluster of the requested size");
-        if (grid > max_clusters) grid = max_clusters;   // fewer teams than slots: the teams loop over the tasks
-        cfg.gridDim = dim3(grid * team);
-        GP_CUDA(ctx, ctx->arena_alloc(reinterpret_cast<void**>(&xi), (size_t)grid * team * 4 * a.n * sizeof(double)));
-        e = cudaLaunchKernelEx(&cfg, ite_kernel<1>, a, ctx->scratch, ctx->slot_scratch_d, ctx->zbuf, ctx->slot_z_d, xi, ctx->counter);
-    }
-    ctx->launches++;
+    GP_CUDA(ctx, ctx->arena_alloc(reinterpret_cast<void**>(&xi), (size_t)grid * team * 4 * a.n * sizeof(double)));
+    int rc = launch_ite_kernel<false>(ctx, a, team, grid, xi);
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) return ctx->cuda_fail(e, "ite_kernel");
+    if (rc) return rc;
     if (e2 != cudaSuccess) return ctx->cuda_fail(e2, "ite_kernel");
     return GPSLC_OK;
 }

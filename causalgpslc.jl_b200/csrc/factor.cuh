@@ -66,6 +66,10 @@ struct __align__(128) FactorSmem {
     double wvec[MAXRHS][NB];           // w_j (pre-solve) / scratch
     double part[4][NB];                // per-row partial sums: log L_ii, z0.z0, z0.z1, z1.z1 (kept out of registers)
     double* snap; int snapJ, snap_n;   // snapshot hook parameters
+    // shared-prefix mode (ITE: chol(Kp) computed once per posterior sample, see factor_run PRE): block rows < pre_split live in the
+    // read-only scratch pre_lo, pre_linv holds the saved P2 outputs of their panels; save_linv: where a factorisation saves them
+    const double* pre_lo; const double* pre_linv; double* save_linv; int pre_split;
+    unsigned int* gbar;                // TEAM = 2: grid-wide barrier state {arrivals, generation}
     double red[32];
     unsigned long long full[STAGES];
     unsigned int freed[STAGES];        // warps that have finished with the slab in each stage (the last one refills it)
@@ -136,12 +140,34 @@ __device__ __forceinline__ uint32_t cluster_count_x() { uint32_t r; asm volatile
 __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// TEAM = 2: every CTA of the (cooperatively launched, hence co-resident) grid works on ONE matrix - the single shared chol(Kp) of a
+// large counterfactual sweep, where even the largest cluster would leave most SMs idle. Sense-reversing barrier on two words of global
+// memory; the caller zeroes them before the launch.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int gen;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");
+        __threadfence();
+        if (atomicAdd(bar, 1u) == gridDim.x - 1) {
+            atomicExch(bar, 0u);
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 1), "r"(gen + 1) : "memory");
+        } else {
+            unsigned int cur;
+            do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(bar + 1) : "memory"); } while (cur == gen);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
 // end-of-phase synchronisation: generic-proxy writes (shared workspace, global L blocks) are ordered before later async-proxy
 // (TMA bulk) reads, by this CTA or — in team mode — by any CTA of the cluster
 template <int TEAM>
-__device__ __forceinline__ void team_sync() {
+__device__ __forceinline__ void team_sync(unsigned int* gbar = nullptr) {
     fence_proxy_async();
-    if constexpr (TEAM != 0) { cluster_barrier(); fence_proxy_async(); }
+    if constexpr (TEAM == 1) { cluster_barrier(); fence_proxy_async(); }
+    else if constexpr (TEAM == 2) { grid_barrier(gbar); fence_proxy_async(); }
     else __syncthreads();
 }
 
@@ -358,6 +384,12 @@ __device__ inline void p2_factor_diag(FactorSmem& sm, double* Cs, int col0) {
 struct Pipe { uint32_t produced; uint32_t consumed; };   // slab sequence numbers of the operand ring (produced is kept equal to
                                                          // consumed at phase boundaries; the ring itself tracks only consumed)
 
+// Start of block row I: rows below sm.pre_split belong to the shared read-only prefix factor, the others to this task's scratch, which
+// then starts at block row pre_split (pre_split == 0: one scratch holds everything).
+__device__ __forceinline__ const double* row_ptr(const FactorSmem& sm, const double* scratch, int I) {
+    return (I < sm.pre_split) ? sm.pre_lo + row_off(I) : scratch + (row_off(I) - row_off(sm.pre_split));
+}
+
 // Row-tile operand producer: slab t of tile `tile` of panel j (A rows of blocks I0 [, I0+1] and the B rows of block j) goes
 // into pipeline slot gi, whose stage must be free. Called by one lane.
 __device__ __forceinline__ void issue_row_slab(FactorSmem& sm, const double* scratch, int j, int T, int blk0, int blk_end, int tile,
@@ -370,13 +402,13 @@ __device__ __forceinline__ void issue_row_slab(FactorSmem& sm, const double* scr
     const size_t so = (size_t)t * SLAB_D;
 #if GPSLC_L2_HINTS
     const uint64_t pa = l2_policy_evict_first(), pb = l2_policy_evict_last();
-    bulk_g2s_hint(dst, scratch + row_off(I0) + so, SLAB_D * 8, &sm.full[st], pa);
-    if (two) bulk_g2s_hint(dst + SLAB_D, scratch + row_off(I0 + 1) + so, SLAB_D * 8, &sm.full[st], pa);
-    bulk_g2s_hint(dst + 2 * SLAB_D, scratch + row_off(j) + so, SLAB_D * 8, &sm.full[st], pb);
+    bulk_g2s_hint(dst, row_ptr(sm, scratch, I0) + so, SLAB_D * 8, &sm.full[st], pa);
+    if (two) bulk_g2s_hint(dst + SLAB_D, row_ptr(sm, scratch, I0 + 1) + so, SLAB_D * 8, &sm.full[st], pa);
+    bulk_g2s_hint(dst + 2 * SLAB_D, row_ptr(sm, scratch, j) + so, SLAB_D * 8, &sm.full[st], pb);
 #else
-    bulk_g2s(dst, scratch + row_off(I0) + so, SLAB_D * 8, &sm.full[st]);
-    if (two) bulk_g2s(dst + SLAB_D, scratch + row_off(I0 + 1) + so, SLAB_D * 8, &sm.full[st]);
-    bulk_g2s(dst + 2 * SLAB_D, scratch + row_off(j) + so, SLAB_D * 8, &sm.full[st]);
+    bulk_g2s(dst, row_ptr(sm, scratch, I0) + so, SLAB_D * 8, &sm.full[st]);
+    if (two) bulk_g2s(dst + SLAB_D, row_ptr(sm, scratch, I0 + 1) + so, SLAB_D * 8, &sm.full[st]);
+    bulk_g2s(dst + 2 * SLAB_D, row_ptr(sm, scratch, j) + so, SLAB_D * 8, &sm.full[st]);
 #endif
 }
 
@@ -564,18 +596,30 @@ __device__ __noinline__ void row_tile_kloop_fold(double* __restrict__ accio, con
 #ifndef GPSLC_FOLD
 #define GPSLC_FOLD 0
 #endif
-template <class Gen, int TEAM = 0, bool SNAP = false, bool FOLD = (GPSLC_FOLD != 0) && !SNAP>
+// PRE (shared prefix): the leading pre_split block rows / panels of the matrix are an already computed factor that several tasks
+// share read-only (ITE: chol(Kp) does not depend on doT, so it is computed once per posterior sample and every doT value continues
+// from it - src/prediction.jl:31-33 redoes it per doT). Panels j < pre_split are REPLAYED: no diagonal tile, no P2 (their outputs
+// come from pre_linv), only the row tiles of this task's own rows (>= pre_split) against the shared B slabs; the caller preloads
+// zbuf[0 .. pre_split*NB) with the prefix's forward solve. `scratch` then holds block rows >= pre_split only.
+// save_linv (any mode): P2's outputs of every panel are also written to save_linv[j][LINV_D] - what a later PRE run replays.
+template <class Gen, int TEAM = 0, bool SNAP = false, bool FOLD = (GPSLC_FOLD != 0) && !SNAP, bool PRE = false>
 __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const int nrhs, double* scratch,
                            double* zbuf /* [MAXRHS][NCB*NB] solves, then [MAXRHS][NCB*NB] pre-solve w */,
-                           FactorSmem& sm, Pipe& pipe, const int snapJ = 1 << 30, double* snap = nullptr, const int snap_n = 0) {
+                           FactorSmem& sm, Pipe& pipe, const int snapJ = 1 << 30, double* snap = nullptr, const int snap_n = 0,
+                           const double* pre_lo = nullptr, const double* pre_linv = nullptr, const int pre_split = 0,
+                           double* save_linv = nullptr) {
     // snapshot hook (SNAP = true, ITE path only — the sampler's instantiation carries none of its code, which matters for the
     // register budget of the k-loops): for panels j >= snapJ the value K - sum_{J<snapJ} L L^T (the Schur complement of the
     // leading snapJ panels, i.e. CovITE + jitter*I) is written to snap[(c-snapJ*NB)*snap_n + (r-snapJ*NB)] (both triangles).
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int npad = NCB * NB;
-    const int trank = TEAM ? (int)cluster_rank() : 0, tsize = TEAM ? (int)cluster_size() : 1;
-    if (tid == 0) { sm.info = 0; sm.snap = snap; sm.snapJ = snapJ; sm.snap_n = snap_n; }
+    const int trank = (TEAM == 1) ? (int)cluster_rank() : (TEAM == 2) ? (int)blockIdx.x : 0;
+    const int tsize = (TEAM == 1) ? (int)cluster_size() : (TEAM == 2) ? (int)gridDim.x : 1;
+    if (tid == 0) {
+        sm.info = 0; sm.snap = snap; sm.snapJ = snapJ; sm.snap_n = snap_n;
+        sm.pre_lo = pre_lo; sm.pre_linv = pre_linv; sm.pre_split = PRE ? pre_split : 0; sm.save_linv = save_linv;
+    }
     if (tid < NB) { sm.part[0][tid] = 0.0; sm.part[1][tid] = 0.0; sm.part[2][tid] = 0.0; sm.part[3][tid] = 0.0; }
     __syncthreads();
 
@@ -584,7 +628,8 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
         const int T = j * NSLAB;  // slabs in the k-loop of this panel
         // Row blocks below the diagonal that this CTA owns. Team mode: the nblk blocks are dealt out in contiguous runs, the ranks
         // that get one block more rotate with the panel index.
-        int nblk = NRB - j - 1, blk0 = j + 1;
+        const bool replay = PRE && j < pre_split;
+        int nblk = replay ? NRB - pre_split : NRB - j - 1, blk0 = replay ? pre_split : j + 1;
         if constexpr (TEAM != 0) {
             const int er = (trank + j) % tsize, per = nblk / tsize, rem = nblk - per * tsize;
             blk0 += er * per + min(er, rem);
@@ -597,7 +642,13 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
         const bool fold2 = fold && (blk0 + 1 < blk_end);      // the folded tile has two blocks (128 rows)
         double accm[2 * 16 + 2 * DSLOTS + MAXRHS];
         // =================================================================== diagonal tile
-        {
+        if (replay) {
+            // shared prefix panel: column features for the generators and the saved P2 outputs; readers of the previous panel's
+            // copies are behind its end-of-panel barrier
+            gen.stage_cols(j * NB, sm.colfeat);
+            for (int i = tid; i < LINV_D; i += FTHREADS) sm.linv[i] = pre_linv[(size_t)j * LINV_D + i];
+            __syncthreads();
+        } else {
             // the 36 lower 8x8 tiles of the diagonal block are dealt 5/4 to the warps (diag_slot); slot s of a warp is tile (srow[s], scol[s])
             const int nslots = (warp < 4) ? 5 : 4;
             int srow[DSLOTS], scol[DSLOTS];
@@ -618,10 +669,10 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                 const int st = gi % STAGES;
                 mbar_expect_tx(&sm.full[st], DS * SLAB_D * 8);
 #if GPSLC_L2_HINTS
-                bulk_g2s_hint(sm.stage + st * STAGE_D + SLAB_D, scratch + row_off(j) + (size_t)t2 * DS * SLAB_D, DS * SLAB_D * 8, &sm.full[st],
+                bulk_g2s_hint(sm.stage + st * STAGE_D + SLAB_D, row_ptr(sm, scratch, j) + (size_t)t2 * DS * SLAB_D, DS * SLAB_D * 8, &sm.full[st],
                               l2_policy_evict_last());     // the row tiles of this panel read the same slabs again
 #else
-                bulk_g2s(sm.stage + st * STAGE_D + SLAB_D, scratch + row_off(j) + (size_t)t2 * DS * SLAB_D, DS * SLAB_D * 8, &sm.full[st]);
+                bulk_g2s(sm.stage + st * STAGE_D + SLAB_D, row_ptr(sm, scratch, j) + (size_t)t2 * DS * SLAB_D, DS * SLAB_D * 8, &sm.full[st]);
 #endif
             };
             if (!fold) {
@@ -746,12 +797,14 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
             GP_PHASE_MARK(5);
             // store L_jj (lower, zeros above), log-diagonal, z_j = L_jj^-1 w_j (rows 64.. of the bordered factorisation)
             {
-                double* dst = scratch + block_off(j, j, NRB);
+                double* dst = const_cast<double*>(row_ptr(sm, scratch, j)) + (size_t)j * BLOCK_D;
                 if (trank == 0) {
                     for (int idx = tid; idx < BLOCK_D; idx += FTHREADS) {
                         const int r = idx >> 6, c = idx & 63;
                         dst[elem_off(r, c)] = (c <= r) ? Cs[r * CS_LD + c] : 0.0;
                     }
+                    if (save_linv)
+                        for (int i = tid; i < LINV_D; i += FTHREADS) save_linv[(size_t)j * LINV_D + i] = sm.linv[i];
                 }
                 if (tid < NB) sm.part[0][tid] += log(Cs[tid * CS_LD + tid]);
                 if (tid < NB * nrhs) {
@@ -858,7 +911,7 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
             //   R_c -= X_b L_cb^T for c > b   (atoms (c, 2b), (c, 2b+1) hold -L_cb)
             // so the 64x64 inverse of L_jj is never formed. A-fragments are rebuilt from accumulator-layout values with quad
             // shuffles (lane (g,q) needs V[g][4h+q], held by lane (g, 2h + q/2), element q%2).
-            double* dst = scratch + block_off(I, j, NRB);
+            double* dst = const_cast<double*>(row_ptr(sm, scratch, I)) + (size_t)j * BLOCK_D;
             auto to_afrag = [&](const double (&t)[2], const int hh) {
                 const int src = (lane & ~3) | (2 * hh + (q >> 1));
                 const double v0 = __shfl_sync(0xffffffffu, t[0], src);
@@ -913,7 +966,7 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
         }
         pipe.produced = pipe.consumed;   // everything issued for this panel has been consumed
         GP_PHASE_MARK(3);
-        team_sync<TEAM>();
+        team_sync<TEAM>(sm.gbar);
         GP_PHASE_MARK(4);
     }
     // ---- reductions

@@ -6,8 +6,8 @@
 
 namespace gpslc {
 
-int ensure_workspace(Ctx* ctx, int NRB, int NCB, long long tasks, int* grid_out, int team) {
-    const size_t need = scratch_doubles(NRB, NCB);
+int ensure_workspace(Ctx* ctx, int NRB, int NCB, long long tasks, int* grid_out, int team, int split) {
+    const size_t need = scratch_doubles(NRB, NCB) - row_off(split);
     const size_t needz = (size_t)2 * MAXRHS * NCB * NB;
     if (ctx->slots == 0) ctx->slots = 2 * ctx->num_sms;   // upper bound on the grid of any factor kernel (sizes per-slot side buffers)
     // Resident factor CTAs per SM for this launch: two, so that one CTA's serial phases overlap the other's tensor work - except
@@ -51,6 +51,19 @@ int ensure_workspace(Ctx* ctx, int NRB, int NCB, long long tasks, int* grid_out,
     ctx->slot_z_d = needz;
     if (!ctx->counter) GP_CUDA(ctx, cudaMalloc(&ctx->counter, 64 * sizeof(unsigned int)));
     *grid_out = (int)grid;
+    return GPSLC_OK;
+}
+
+int ensure_zbuf(Ctx* ctx, int NCB, long long ctas) {
+    const size_t needz = (size_t)2 * MAXRHS * NCB * NB;
+    if ((size_t)ctas * needz > ctx->z_cap_d) {
+        if (ctx->zbuf) cudaFree(ctx->zbuf);
+        ctx->zbuf = nullptr; ctx->z_cap_d = 0;
+        GP_CUDA(ctx, cudaMalloc(&ctx->zbuf, (size_t)ctas * needz * sizeof(double)));
+        ctx->z_cap_d = (size_t)ctas * needz;
+    }
+    ctx->slot_z_d = needz;
+    if (!ctx->counter) GP_CUDA(ctx, cudaMalloc(&ctx->counter, 64 * sizeof(unsigned int)));
     return GPSLC_OK;
 }
 

@@ -523,6 +523,42 @@ def test_ite_cluster_teams_match_single_cta(ctx, monkeypatch):
                 assert np.array_equal(ref[key], outs[team][key]), (n, team, key)
 
 
+def test_ite_shared_kp_factor_matches_one_cholesky_per_task(ctx, monkeypatch):
+    """Several doT values per posterior sample (predictCounterfactualEffects): chol(Kp), L11^-1 Y and the panels' P2 outputs are computed
+    once per (chain, sample) and every doT continues from them (factor.cuh PRE, ite_base_kernel) instead of re-factoring Kp inside
+    every augmented matrix. Same arithmetic in the same order, so MeanITE, CovITE, draws and info must be BIT-identical to the fused
+    path (GPSLC_ITE_SHARE=0), for one-CTA tasks, cluster teams, and the grid-wide factorisation of a single large sample."""
+    cases = [(40, 4, 2, 2, 2, None), (300, 6, 3, 2, 2, "2"), (521, 1, 2, 1, 1, "4"), (1100, 4, 3, 1, 1, None)]
+    for n, n_obj, nX, C, R, team in cases:
+        counts, X, T, Y = od.synthetic(n - n % n_obj, n_obj, nX, seed=23)
+        nn = len(T)
+        spec = om.ModelSpec(nn, 1, nX, False)
+        rng = np.random.default_rng(n)
+        smp = np.ones((R, C, spec.n_params + nn))
+        smp[:, :, :spec.n_params] = 0.7 + 0.6 * rng.random((R, C, spec.n_params))
+        smp[:, :, 2] = 0.25
+        smp[:, :, spec.n_params:] = np.repeat(rng.standard_normal((R, C, n_obj)), nn // n_obj, axis=2)
+        ret = np.arange(R, dtype=np.int32)
+        doTs = (0.3, -0.4, 1.1)
+        if team:
+            monkeypatch.setenv("GPSLC_TEAM", team)
+        monkeypatch.setenv("GPSLC_ITE_SHARE", "0")
+        ref = ge.ite(smp, X, T, Y, 1, doTs, ret, 1e-10, 3, seed=6, want_cov=(nn < 600), ctx=ctx)
+        monkeypatch.setenv("GPSLC_ITE_SHARE", "1")
+        got = ge.ite(smp, X, T, Y, 1, doTs, ret, 1e-10, 3, seed=6, want_cov=(nn < 600), ctx=ctx)
+        monkeypatch.delenv("GPSLC_ITE_SHARE")
+        if team:
+            monkeypatch.delenv("GPSLC_TEAM")
+        assert ref["info"].max() == 0 and got["info"].max() == 0
+        for key in ("mean", "cov", "samples", "info"):
+            if ref[key] is not None:
+                assert np.array_equal(ref[key], got[key]), (n, key, np.abs(ref[key] - got[key]).max())
+    # a posterior sample whose Kp is not positive definite fails in the shared factor: every doT of that sample reports it
+    smp[0, 0, 2] = -30.0
+    bad = ge.ite(smp, X, T, Y, 1, doTs, ret, 1e-10, 2, ctx=ctx)
+    assert np.all(bad["info"][:, 0, 0] >= 1)
+
+
 def test_zero_effect_identity_through_c_abi(ctx, kats):
     """doT == T => MeanITE == 0 and CovITE == jitter exactly, for U/X present or absent (test/estimation.jl:6-247)."""
     k = kats["conditionalITE_zero_effect"]
