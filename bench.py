@@ -375,8 +375,8 @@ def run_ours(args):
             extra[name] = {"value": world * C2 * st2 / (msx * 1e-3), "unit": "sweeps/s", "ms_per_step": msx / st2, "steps": st2, "warmup": wu2,
                            "tflops_per_gpu": tf, "frac": tf / peak,
                            "workload": f"n={n2}, {nobj2} objects, nX={nX2}, nU=1, {C2} chains per GPU, {Sx} sites per sweep"}
-        if world == 8:
-            extra["c5"] = run_c5(g, ge, ctx, rank, world, pri, peak, barrier, max_over_ranks)
+        if world == 8 or os.environ.get("GPSLC_BENCH_C5"):       # the env switch runs a proportional share (32 doT per GPU) at any N
+            extra["c5"] = run_c5(g, ge, ctx, rank, world, pri, peak, barrier, max_over_ranks, n_dot=32 * world)
 
     if rank == 0:
         n = w["n"]

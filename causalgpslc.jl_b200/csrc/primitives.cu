@@ -261,6 +261,7 @@ int launch_cov_build(Ctx* ctx, int n, int batch, int D, const double* f1, const 
         const int nt = ceil_div(n, 64);
         dim3 grid(nt * (nt + 1) / 2, 1, batch);
         const size_t sh = (size_t)(32 + 2 * D * 64) * sizeof(double);
+        if (sh > 48 * 1024) GP_CUDA(ctx, cudaFuncSetAttribute(cov_build_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
         cov_build_sym_kernel<<<grid, 256, sh, ctx->stream>>>(n, D, f1, feat_stride, w, scale, noise, noise != nullptr, K);
         ctx->launches++;
         GP_CUDA(ctx, cudaGetLastError());
@@ -268,6 +269,7 @@ int launch_cov_build(Ctx* ctx, int n, int batch, int D, const double* f1, const 
     }
     dim3 grid(ceil_div(n, 128), ceil_div(n, 32), batch);
     size_t sh = (size_t)(32 + D * 32 + D * 128) * sizeof(double);
+    if (sh > 48 * 1024) GP_CUDA(ctx, cudaFuncSetAttribute(cov_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
     cov_build_kernel<<<grid, 256, sh, ctx->stream>>>(n, D, f1, f2, feat_stride, w, scale, noise, noise != nullptr, K);
     ctx->launches++;
     GP_CUDA(ctx, cudaGetLastError());

@@ -259,6 +259,34 @@ function predictCounterfactualEffectsShard(g, nSamplesPerMixture::Int, world_siz
 end
 
 """
+    predictCounterfactualSummaryShard(g, nSamplesPerMixture, world_size, rank; fidelity=100, minDoT, maxDoT, credible_interval=0.90)
+predictCounterfactualEffects (src/prediction.jl:23-36) followed by summarizeEstimates (src/driver.jl:129-149) per doT, fused on the
+device through gpslc_ite_summary: the ITE draws of this rank's block of doT values never leave HBM (BASELINE c5: 168 MB of draws), only
+`summary[3, n, d_local]` = (Mean, LowerBound, UpperBound) per individual and doT comes back. Returns (summary, doTrange, offset).
+"""
+function predictCounterfactualSummaryShard(g, nSamplesPerMixture::Int, world_size::Int, rank::Int; fidelity::Int=100,
+                                           minDoT=min(g.T...), maxDoT=max(g.T...), seed=UInt64(0), credible_interval::Float64=0.90)
+    doTrange = minDoT:(abs(maxDoT - minDoT) / fidelity):maxDoT
+    all = collect(Float64, doTrange); D = length(all)
+    base, rem = divrem(D, world_size)
+    cnt = base + (rank < rem ? 1 : 0); off = rank * base + min(rank, rem)
+    dts = all[off+1:off+cnt]
+    packed = pack(g); ret = retained(g.hyperparams); R = length(ret); n = length(g.Y)
+    Tf = Float64.(g.T); Xf = g.X === nothing ? Float64[] : Matrix{Float64}(g.X); Yf = Float64.(g.Y)
+    out = Array{Float64}(undef, 3, n, cnt)                           # C layout [d_local][1][n][3]
+    info = zeros(Cint, R * cnt)
+    GC.@preserve packed ret Tf Xf Yf out dts info begin
+        check(ccall((:gpslc_ite_summary, LIB[]), Cint,
+                    (Ptr{Cvoid}, Cint, Ref{GpslcData}, Ptr{Cdouble}, Cint, Cint, Cint, Ptr{Cint}, Cint, Ptr{Cdouble}, Cint, Cint, Cdouble,
+                     Cint, UInt64, Cint, Cdouble, Ptr{Cdouble}, Ptr{Cint}),
+                    CTX[], 0, data_struct(g, Tf, Xf, Yf), packed, size(packed, 3), 1, size(packed, 1), ret, R, dts, cnt, off,
+                    g.hyperparams.predictionCovarianceNoise, nSamplesPerMixture, seed, 0, credible_interval, out, info))
+    end
+    check_info(info)
+    out, doTrange, off
+end
+
+"""
     summarizeEstimates(samples; credible_interval=0.90) — the statistics of src/driver.jl:129-149 (row mean and the two
 quantiles, Julia `quantile` default) through gpslc_summarize. `samples` is the n × m matrix sampleITE returns, whose memory
 is exactly the C layout [m][n]. Returns (Mean, LowerBound, UpperBound) vectors; the DataFrame/CSV part stays in driver.jl.

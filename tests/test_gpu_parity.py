@@ -70,6 +70,29 @@ def test_chol_logpdf_vs_oracle(ctx, n):
     assert abs(lp3[0] - want[0]) <= 1e-10 * abs(want[0])
 
 
+def test_many_feature_dimensions(ctx):
+    """More than 24 feature dimensions: the panel's column features no longer fit the shared-memory staging area and are read from
+    global memory (same values); up to 64 dimensions (nU + nX + 1) are supported, more are refused loudly."""
+    rng = np.random.default_rng(11)
+    n, batch = 150, 2
+    for D in (25, 40, 64):
+        F = rng.standard_normal((n, D)); ls = 2.0 + 3 * rng.random((batch, D)); sc = 0.5 + rng.random(batch); nz = 0.05 + rng.random(batch)
+        y = rng.standard_normal((batch, n))
+        want = np.array([om.mvn_logpdf_chol(y[b], ok.process_cov(ok.rbf_kernel_log(F, F, ls[b]), sc[b], nz[b])) for b in range(batch)])
+        lp, ld, q, info = g.rbf_logpdf(F, ls, sc, nz, y, ctx=ctx)
+        assert np.all(info == 0) and np.max(np.abs(lp - want) / np.abs(want)) <= 1e-10
+        K = g.cov_build(F, F, ls, sc, nz, ctx=ctx)
+        assert np.max(np.abs(K[0] - ok.process_cov(ok.rbf_kernel_log(F, F, ls[0]), sc[0], nz[0]))) <= 4 * np.finfo(float).eps * (sc[0] + nz[0])
+    counts, X, T, Y = od.synthetic(60, 3, 30, seed=4)          # Y factor: 32 dimensions
+    md = od.model_data_from_arrays(counts, X, T, Y, nU=1)
+    *_, got, acc, ev = _run_pair(md, X, T, Y, counts, 2, 1, 1, 3, 1)
+    want, _ = oi.posterior(md, 2, 1, 1, seed=3, chain=0)
+    assert np.allclose(np.nan_to_num(want), np.nan_to_num(got[:, 0, :]), rtol=1e-8, atol=1e-11)
+    with pytest.raises(g.GpslcError) as ei:
+        g.rbf_logpdf(rng.standard_normal((n, 65)), np.ones((1, 65)), [1.0], [0.1], rng.standard_normal((1, n)), ctx=ctx)
+    assert ei.value.code == 2
+
+
 def test_chol_not_positive_definite_reports_lapack_info(ctx):
     K = np.eye(70); K[40, 40] = -1.0
     lp, ld, q, info = g.chol_logpdf(K[None], np.ones(70), ctx=ctx)
