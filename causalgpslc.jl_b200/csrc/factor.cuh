@@ -26,7 +26,8 @@ namespace gpslc {
 // Development aid (-DGPSLC_PHASE_TIMING, tools/gpu_phase_timing.py): cycles thread 0 of every CTA spends in each phase of
 // factor_run, accumulated in a per-translation-unit device array. Compiles to nothing in the product build.
 #ifdef GPSLC_PHASE_TIMING
-static __device__ unsigned long long g_phase_cycles[24];
+static __device__ unsigned long long g_phase_cycles[64];   // 24..31 end-of-panel barrier wait per warp, 32..39 row k-loop time per warp,
+                                                          // 40..47 operand wait per warp, 48..55 stage refills issued per warp
 #define GP_PHASE_INIT() long long _pt = clock64()
 #define GP_PHASE_MARK(k) do { if (threadIdx.x == 0) { const long long _n = clock64(); atomicAdd(&g_phase_cycles[k], (unsigned long long)(_n - _pt)); _pt = _n; } } while (0)
 #else
@@ -438,7 +439,7 @@ __device__ __noinline__ void row_tile_kloop(double* __restrict__ accio, const do
         }
     uint32_t gi = gi0;
 #ifdef GPSLC_PHASE_TIMING
-    long long _wait = 0, _prod = 0;
+    long long _wait = 0, _prod = 0, _nref = 0;
     const long long _f0 = clock64();
 #endif
     const int fbase = tile * T + STAGES;
@@ -475,7 +476,7 @@ __device__ __noinline__ void row_tile_kloop(double* __restrict__ accio, const do
 #endif
             issue_row_slab(sm, scratch, j, T, blk0, blk_end, ptile, pt, gi + STAGES);
 #ifdef GPSLC_PHASE_TIMING
-            _prod += clock64() - _p0;
+            _prod += clock64() - _p0; _nref++;
 #endif
         }
     }
@@ -491,6 +492,9 @@ __device__ __noinline__ void row_tile_kloop(double* __restrict__ accio, const do
         atomicAdd(&g_phase_cycles[12], (unsigned long long)_wait);
         atomicAdd(&g_phase_cycles[13], (unsigned long long)(clock64() - _f0));
         atomicAdd(&g_phase_cycles[14], (unsigned long long)_prod);
+        atomicAdd(&g_phase_cycles[32 + warp], (unsigned long long)(clock64() - _f0));
+        atomicAdd(&g_phase_cycles[40 + warp], (unsigned long long)_wait);
+        atomicAdd(&g_phase_cycles[48 + warp], (unsigned long long)_nref);
     }
 #endif
 }
@@ -966,7 +970,13 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
         }
         pipe.produced = pipe.consumed;   // everything issued for this panel has been consumed
         GP_PHASE_MARK(3);
+#ifdef GPSLC_PHASE_TIMING
+        const long long _b0 = clock64();
+#endif
         team_sync<TEAM>(sm.gbar);
+#ifdef GPSLC_PHASE_TIMING
+        if (lane == 0) atomicAdd(&g_phase_cycles[24 + warp], (unsigned long long)(clock64() - _b0));
+#endif
         GP_PHASE_MARK(4);
     }
     // ---- reductions

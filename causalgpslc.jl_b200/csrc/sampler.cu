@@ -407,8 +407,8 @@ mh_lanes_kernel(ModelDev m, ChainDev c, const int* lane_order, int outer, int j0
 }  // namespace gpslc
 extern "C" int gpslc_debug_phase_cycles(unsigned long long* out8, int reset) {
     cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out8, gpslc::g_phase_cycles, 24 * sizeof(unsigned long long));
-    if (reset) { unsigned long long z[24] = {0}; cudaMemcpyToSymbol(gpslc::g_phase_cycles, z, sizeof(z)); }
+    cudaMemcpyFromSymbol(out8, gpslc::g_phase_cycles, 64 * sizeof(unsigned long long));
+    if (reset) { unsigned long long z[64] = {0}; cudaMemcpyToSymbol(gpslc::g_phase_cycles, z, sizeof(z)); }
     return 0;
 }
 namespace gpslc {

@@ -13,7 +13,7 @@ counts, X, T, Y = synthetic(n, n_obj, nX)
 ctx = g.Context(0)
 smp = ChainSampler(default_priors(), X, T, Y, 1, counts, nOuter=24, nMHInner=10, nESInner=5, n_chains=C, seed=1234, ctx=ctx)
 smp.mh_sweeps(1); ctx.synchronize()
-out = (ctypes.c_ulonglong * 24)()
+out = (ctypes.c_ulonglong * 64)()
 ctx.lib.gpslc_debug_phase_cycles(out, 1)
 smp.mh_sweeps(2); ctx.synchronize()
 ctx.lib.gpslc_debug_phase_cycles(out, 1)
@@ -29,3 +29,6 @@ print(f"  {'outside factor_run':40s} {100 * (tot - v[[0, 1, 5, 6, 2, 3, 4]].sum(
 print(f"  row k-loop, per-warp average: waiting for operands (full barrier) {100 * v[12] / v[13]:.2f} % of the loop, "
       f"elected producer (empty barrier + TMA issue) {100 * v[14] / v[13]:.2f} %")
 print(f"  8x8 potf2 (warp 0): loads {100 * v[16] / tot:.2f} %, factor loop {100 * v[17] / tot:.2f} %, inverse loop {100 * v[18] / tot:.2f} %, stores {100 * v[19] / tot:.2f} % of the CTA's time")
+print("  per warp, fraction of the CTA's kernel time: end-of-panel barrier wait / row k-loop total / operand (mbarrier) wait; stage refills issued")
+for w in range(8):
+    print(f"    warp {w}: barrier {100 * v[24 + w] / tot:5.2f} %   k-loop {100 * v[32 + w] / tot:5.2f} %   operand wait {100 * v[40 + w] / tot:5.2f} %   refills {int(v[48 + w])}")
