@@ -426,6 +426,7 @@ static int launch_ite_kernel(Ctx* ctx, const EstArgs& a, int team, int grid, dou
         return GPSLC_OK;
     }
     GP_CUDA(ctx, cudaFuncSetAttribute(ite_kernel<1, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
+    if (team > 8) GP_CUDA(ctx, cudaFuncSetAttribute(ite_kernel<1, PRE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -443,6 +444,7 @@ static int launch_ite_kernel(Ctx* ctx, const EstArgs& a, int team, int grid, dou
 template <class K>
 static int clip_to_resident_clusters(Ctx* ctx, K k, int team, int grid, int* out) {
     GP_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
+    if (team > 8) GP_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -528,6 +530,7 @@ static int launch_ite_shared(Ctx* ctx, const EstArgs& a0) {
         {
             const long long total = (long long)a.n_doT * nb;
             int team = pick_team(ctx, total, NCB);
+            if (const char* e = getenv("GPSLC_ITE_TEAM")) { const int g = atoi(e); if (g >= 1 && g <= 16) team = g; }   // development knob; > 8 = non-portable cluster
             int grid = 0;
             GP_TRY(ensure_workspace(ctx, NCB, NCB, total, &grid, team, NCB1));
             if (team > 1) GP_TRY(clip_to_resident_clusters(ctx, ite_kernel<1, true>, team, grid, &grid));
