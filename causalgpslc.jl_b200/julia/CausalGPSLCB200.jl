@@ -317,12 +317,39 @@ end
 # object, which only Julia can read). Layout: 8-byte magic "GPSLCB2\0", little-endian UInt64 header length, JSON header
 # {"version","hyperparams","priorparams","seed","arrays":[{"name","dtype","shape"}...]}, then the arrays raw, C order, each padded
 # to 8 bytes. Only the packed posterior samples are needed to rebuild g.posteriorSamples (to_choicemap).
-"write the packed samples [stride, n_chains, nOuter] of a run next to the data, readable by loadGPSLCObject of the Python mirror"
-function savePacked(filename::String, packed::Array{Float64,3}, header_json::String, arrays::Vector{Pair{String,Array}})
-    if length(filename) > 6 && filename[end-5:end] == ".gpslc"; filename = filename[1:end-6]; end       # src/io.jl:15-17
+json_num(x) = x === nothing ? "null" : (x isa Bool ? (x ? "true" : "false") : (x isa Integer ? string(x) : repr(Float64(x))))
+np_dtype(::Type{Float64}) = "<f8"; np_dtype(::Type{Bool}) = "|b1"; np_dtype(::Type{Int64}) = "<i8"
+
+"""
+    savePacked(filename, g, packed; seed=0)
+Write `g` (a GPSLCObject) with the packed posterior samples `packed` [stride, n_chains, nOuter] (second return value of `Posterior`)
+as a `.gpslc` container that `gpslc_b200.loadGPSLCObject` (Python mirror) reads: data arrays in C order, SigmaU as object counts when
+it has the generateSigmaU structure. The `.gpslc` extension is optional (src/io.jl:15-17).
+"""
+function savePacked(filename::String, g, packed::Array{Float64,3}; seed::Integer=0)
+    if length(filename) > 6 && filename[end-5:end] == ".gpslc"; filename = filename[1:end-6]; end
+    h = g.hyperparams
+    arrays = Pair{String,Array}["packed" => packed, "T" => (eltype(g.T) == Bool ? Vector{Bool}(g.T) : Float64.(g.T)), "Y" => Float64.(g.Y)]
+    shapes = Dict("packed" => reverse(size(packed)), "T" => (length(g.T),), "Y" => (length(g.Y),))
+    if g.X !== nothing
+        push!(arrays, "X" => permutedims(Matrix{Float64}(g.X)))             # C order [n][nX] == column-major [nX, n]
+        shapes["X"] = size(g.X)
+    end
+    if g.SigmaU !== nothing
+        st = sigmaUstructure(Matrix{Float64}(g.SigmaU))
+        if st === nothing
+            push!(arrays, "SigmaU" => Matrix{Float64}(g.SigmaU)); shapes["SigmaU"] = size(g.SigmaU)      # symmetric: order irrelevant
+        else
+            push!(arrays, "obj_counts" => Int64.(st[1])); shapes["obj_counts"] = (length(st[1]),)
+        end
+    end
+    hp = join(["\"$k\": " * json_num(getfield(h, k)) for k in (:nU, :nOuter, :nMHInner, :nESInner, :nBurnIn, :stepSize, :predictionCovarianceNoise)], ", ")
+    pp = join(["\"$k\": " * json_num(v) for (k, v) in g.priorparams if v isa Real], ", ")
+    arr = join(["{\"name\": \"$(nm)\", \"dtype\": \"$(np_dtype(eltype(a)))\", \"shape\": [$(join(shapes[nm], ", "))]}" for (nm, a) in arrays], ", ")
+    header = "{\"version\": 1, \"hyperparams\": {$hp}, \"priorparams\": {$pp}, \"seed\": $(Int(seed)), \"arrays\": [$arr]}"
     open(filename * ".gpslc", "w") do io
-        write(io, b"GPSLCB2\0"); write(io, htol(UInt64(sizeof(header_json)))); write(io, header_json)
-        for (_, a) in vcat(["packed" => packed], arrays)
+        write(io, b"GPSLCB2\0"); write(io, htol(UInt64(sizeof(header)))); write(io, header)
+        for (_, a) in arrays
             write(io, a); write(io, zeros(UInt8, mod(-sizeof(a), 8)))
         end
     end
