@@ -234,6 +234,12 @@ __device__ __forceinline__ double rsqrt_fast(double a) {
 }
 __device__ __forceinline__ double neg_bits(double x) { return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x)); }
 
+// GPSLC_PIVOT_RCP = 1: pivot recurrence through the reciprocal (4 dependent FP64 instructions per pivot instead of 7). Measured on
+// B200, same box back to back: c3 1279.6 vs 1285.8 sweeps/s, c2 50.0 k vs 50.9 k - no gain (the pivot warp is not limited by the
+// length of that chain but by issue slots behind the sibling CTA's DMMA stream), so it is off.
+#ifndef GPSLC_PIVOT_RCP
+#define GPSLC_PIVOT_RCP 0
+#endif
 __device__ inline void p2_factor_diag(FactorSmem& sm, double* Cs, int col0) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
@@ -278,9 +284,24 @@ __device__ inline void p2_factor_diag(FactorSmem& sm, double* Cs, int col0) {
                 if (lane == 0 && sm.info == 0) sm.info = col0 + c0 + k + 1;
                 akk = 1.0;
             }
+#if GPSLC_PIVOT_RCP
+            // The chain from one pivot to the next goes through the RECIPROCAL, a_{k+1,k+1} - a_{k+1,k}^2 / a_kk: hardware seed and one
+            // third-order step y (1 + e + e^2), e = 1 - a y (relative error seed^3 ~ 2^-60 before rounding), then one fma - four
+            // dependent FP64 instructions instead of the seven of rsqrt -> multiply -> fma. 1/sqrt(a_kk), which scales the column, is
+            // computed beside it and feeds only the column update, which has a pivot period of slack.
+            double yr;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(yr) : "d"(akk));
+            const double er = fma(-akk, yr, 1.0);
+            const double pr = fma(er, er, er);
+            const double rcp = fma(yr, pr, yr);
+            const double q10 = d10 * d10;
+            const double ri = rsqrt_fast(akk);
+            akk = fma(-q10, rcp, d11);          // next pivot
+#else
             const double ri = rsqrt_fast(akk);
             const double l10 = d10 * ri;
             akk = fma(-l10, l10, d11);          // next pivot
+#endif
             const double lk = a[k] * ri;
             a[k] = lk;
             if (lane < 8) colbuf[k * 8 + r] = lk;
