@@ -576,6 +576,23 @@ def test_ite_shared_kp_factor_matches_one_cholesky_per_task(ctx, monkeypatch):
         for key in ("mean", "cov", "samples", "info"):
             if ref[key] is not None:
                 assert np.array_equal(ref[key], got[key]), (n, key, np.abs(ref[key] - got[key]).max())
+    # model variants: no U / no X / neither, Boolean treatment (doT in {0, 1})
+    _, X2, T2, Y2 = od.synthetic(150, 6, 2, seed=29)
+    for nU, Xv, Tv, dv in ((0, X2, T2, (0.2, 0.9)), (1, None, T2, (0.2, 0.9)), (0, None, T2, (0.2, 0.9, -1.0)), (1, X2, T2 > np.median(T2), (1.0, 0.0))):
+        nX = 0 if Xv is None else Xv.shape[1]
+        spec = om.ModelSpec(150, nU, nX, False)
+        rec = np.ones((2, 1, spec.n_params + nU * 150))
+        rec[:, :, :spec.n_params] = 0.7 + 0.6 * np.random.default_rng(nU + 3 * nX).random((2, 1, spec.n_params))
+        rec[:, :, 2] = 0.25
+        ret2 = np.arange(2, dtype=np.int32)
+        monkeypatch.setenv("GPSLC_ITE_SHARE", "0")
+        ref = ge.ite(rec, Xv, Tv, Y2, nU, dv, ret2, 1e-10, 2, seed=3, want_cov=True, ctx=ctx)
+        monkeypatch.setenv("GPSLC_ITE_SHARE", "1")
+        got = ge.ite(rec, Xv, Tv, Y2, nU, dv, ret2, 1e-10, 2, seed=3, want_cov=True, ctx=ctx)
+        monkeypatch.delenv("GPSLC_ITE_SHARE")
+        assert ref["info"].max() == 0
+        for key in ("mean", "cov", "samples", "info"):
+            assert np.array_equal(ref[key], got[key]), (nU, nX, key)
     # a posterior sample whose Kp is not positive definite fails in the shared factor: every doT of that sample reports it
     smp[0, 0, 2] = -30.0
     bad = ge.ite(smp, X, T, Y, 1, doTs, ret, 1e-10, 2, ctx=ctx)
