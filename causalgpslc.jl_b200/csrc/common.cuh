@@ -13,7 +13,10 @@
 
 namespace gpslc {
 
-constexpr int DMAX = 64;        // max feature dimensions of one covariance factor (nU + nX + 1); beyond CF_DIMS (24) the column
+#ifndef GPSLC_DMAX
+#define GPSLC_DMAX 64
+#endif
+constexpr int DMAX = GPSLC_DMAX;        // max feature dimensions of one covariance factor (nU + nX + 1); beyond CF_DIMS (24) the column
                                 // features of a panel are read from global memory instead of shared memory (slower, same values)
 constexpr double LOG_2PI = 1.8378770664093454835606594728112;
 

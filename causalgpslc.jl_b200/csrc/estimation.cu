@@ -53,7 +53,7 @@ struct IteGen {
         if (on_diag) val = __dadd_rn(val, c2 ? s->jitter : s->yNoise);
         return val;
     }
-    __device__ __forceinline__ double one(int r, int c) const {
+    __device__ __noinline__ double one(int r, int c) const {      // ragged edges and the diagonal snapshot only (code size, see RbfGen::one)
         const int n = s->n, np = s->npad;
         const bool r2 = r >= np, c2 = c >= np;
         const int i = r2 ? r - np : r, j = c2 ? c - np : c;
@@ -179,7 +179,7 @@ __device__ inline void fill_ite_spec(const EstArgs& a, const double* rec, double
 // continues from for every doT value. TEAM = 1: one cluster per base task; TEAM = 2: the whole cooperatively launched grid on one base
 // task after the other (few large samples: the n = 8192 sweep has ONE).
 template <int TEAM>
-__global__ void __launch_bounds__(FTHREADS, 2)
+__global__ void __launch_bounds__(FTHREADS, CTAS_PER_SM)
 ite_base_kernel(EstArgs a, double* base_L, double* base_linv, double* base_z, int* base_info, double* zbuf, size_t slot_z,
                 unsigned int* counter, unsigned int* gbar) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -221,7 +221,7 @@ ite_base_kernel(EstArgs a, double* base_L, double* base_linv, double* base_z, in
 }
 
 template <int TEAM, bool PRE = false>
-__global__ void __launch_bounds__(FTHREADS, 2)
+__global__ void __launch_bounds__(FTHREADS, CTAS_PER_SM)
 ite_kernel(EstArgs a, double* scratch, size_t slot_scratch, double* zbuf, size_t slot_z, double* xibuf, unsigned int* counter) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FactorSmem& sm = *reinterpret_cast<FactorSmem*>(smem_raw);
@@ -311,7 +311,7 @@ ite_kernel(EstArgs a, double* scratch, size_t slot_scratch, double* zbuf, size_t
 }
 
 // SATE fast path: one task = (doT, chain, retained sample)
-__global__ void __launch_bounds__(FTHREADS, 2)
+__global__ void __launch_bounds__(FTHREADS, CTAS_PER_SM)
 sate_kernel(EstArgs a, double* scratch, size_t slot_scratch, double* zbuf, size_t slot_z, double* d1buf, unsigned int* counter) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FactorSmem& sm = *reinterpret_cast<FactorSmem*>(smem_raw);

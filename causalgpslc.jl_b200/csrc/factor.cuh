@@ -41,7 +41,11 @@ constexpr int K4S = KB / 4;            // 8x4 operand atoms along k per slab
 constexpr int NSLAB = NB / KB;         // slabs per block
 constexpr int SLAB_D = NB * KB;        // doubles per slab (8 KB)
 constexpr int BLOCK_D = NB * NB;       // doubles per block (32 KB)
-constexpr int STAGES = 3;
+#ifndef GPSLC_CTAS
+#define GPSLC_CTAS 2           // resident factor CTAs per SM the kernels are built for (3: experiment with a two-stage operand ring)
+#endif
+constexpr int CTAS_PER_SM = GPSLC_CTAS;
+constexpr int STAGES = (GPSLC_CTAS >= 3) ? 2 : 3;
 constexpr int FWARPS = 8;
 constexpr int FTHREADS = FWARPS * 32;
 constexpr int STAGE_D = 3 * SLAB_D;    // A0 | A1 | B
@@ -49,7 +53,7 @@ constexpr int MAXRHS = 2;
 constexpr int CS_LD = 66;              // P2 workspace leading dimension (16-byte aligned rows)
 constexpr int CS_ROWS = 72;            // 64 matrix rows + up to MAXRHS right-hand-side rows + zero padding to a full 8-row tile
 constexpr int LINV_D = 72 * 32;        // atoms (n8, k4) with k4 <= 2*n8+1, row n8 starts at atom n8*(n8+1)
-constexpr int CF_DIMS = 24;            // feature dimensions staged per panel (more dimensions fall back to global loads)
+constexpr int CF_DIMS = (GPSLC_CTAS >= 3) ? 4 : 24;   // feature dimensions staged per panel (more dimensions fall back to global loads)
 
 struct FactorOut {
     double logdet;      // log det K

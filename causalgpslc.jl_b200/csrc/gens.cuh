@@ -83,7 +83,9 @@ struct RbfSpec {
 struct RbfGen {
     const RbfSpec* s;
     const double* tab;          // FactorSmem::exp2tab
-    __device__ __forceinline__ double one(int r, int c) const {
+    // element-wise path (ragged edges only): deliberately NOT inlined - sixteen inlined copies per strip instance were half of the
+    // sampler kernel's 290 KB of code, and at small n the instruction fetch misses show up as `no_instruction` stalls
+    __device__ __noinline__ double one(int r, int c) const {
         if (r >= s->n || c >= s->n) return (r == c) ? 1.0 : 0.0;
         double a = 0.0;
         for (int d = 0; d < s->D; d++) {
@@ -111,48 +113,27 @@ struct RbfGen {
     template <int NI, bool ONE_ROW>
     __device__ __forceinline__ void strip(int r0, int r1, int c0, double (&v)[2][NI][2], const double* cf, int cl) const {
         const int n = s->n;
-        if (r1 < n && r0 < n && c0 + 8 * (NI - 1) + 1 < n) {
+        const int D = s->D;
+        // fast path: all entries inside the matrix and the panel's column features staged in shared memory (D <= CF_DIMS); otherwise
+        // (ragged edge, or more dimensions than the staging area holds) the element-wise path below, which gives the same values
+        if (r1 < n && r0 < n && c0 + 8 * (NI - 1) + 1 < n && GPSLC_STAGE_COLS && D <= CF_DIMS) {
             double a[2][NI][2];
 #pragma unroll
             for (int ni = 0; ni < NI; ni++) { a[0][ni][0] = 0.0; a[0][ni][1] = 0.0; a[1][ni][0] = 0.0; a[1][ni][1] = 0.0; }
-            const int D = s->D;
-            const bool staged = GPSLC_STAGE_COLS && (D <= CF_DIMS);
-            // two separate loops (not one loop with a branch inside): ptxas if-converted the inner branch and executed the
-            // global loads and multiplies of the unstaged path speculatively on every iteration
-            if (staged) {
-#pragma unroll 4
-                for (int d = 0; d < D; d++) {
-                    const double w = s->sw[d];
-                    const double z0 = __dmul_rn(__ldg(s->feat[d] + r0), w);
-                    const double z1 = ONE_ROW ? z0 : __dmul_rn(__ldg(s->feat[d] + r1), w);
+#pragma unroll 2
+            for (int d = 0; d < D; d++) {
+                const double w = s->sw[d];
+                const double z0 = __dmul_rn(__ldg(s->feat[d] + r0), w);
+                const double z1 = ONE_ROW ? z0 : __dmul_rn(__ldg(s->feat[d] + r1), w);
 #pragma unroll
-                    for (int ni = 0; ni < NI; ni++) {
-                        const double2 cc = *reinterpret_cast<const double2*>(cf + d * NB + cl + 8 * ni);
-                        double t;
-                        t = __dsub_rn(z0, cc.x); a[0][ni][0] = __fma_rn(t, t, a[0][ni][0]);
-                        t = __dsub_rn(z0, cc.y); a[0][ni][1] = __fma_rn(t, t, a[0][ni][1]);
-                        if (!ONE_ROW) {
-                            t = __dsub_rn(z1, cc.x); a[1][ni][0] = __fma_rn(t, t, a[1][ni][0]);
-                            t = __dsub_rn(z1, cc.y); a[1][ni][1] = __fma_rn(t, t, a[1][ni][1]);
-                        }
-                    }
-                }
-            } else {
-                for (int d = 0; d < D; d++) {
-                    const double* p = s->feat[d];
-                    const double w = s->sw[d];
-                    const double z0 = __dmul_rn(__ldg(p + r0), w);
-                    const double z1 = ONE_ROW ? z0 : __dmul_rn(__ldg(p + r1), w);
-#pragma unroll
-                    for (int ni = 0; ni < NI; ni++) {
-                        const double c0v = __dmul_rn(__ldg(p + c0 + 8 * ni), w), c1v = __dmul_rn(__ldg(p + c0 + 8 * ni + 1), w);
-                        double t;
-                        t = __dsub_rn(z0, c0v); a[0][ni][0] = __fma_rn(t, t, a[0][ni][0]);
-                        t = __dsub_rn(z0, c1v); a[0][ni][1] = __fma_rn(t, t, a[0][ni][1]);
-                        if (!ONE_ROW) {
-                            t = __dsub_rn(z1, c0v); a[1][ni][0] = __fma_rn(t, t, a[1][ni][0]);
-                            t = __dsub_rn(z1, c1v); a[1][ni][1] = __fma_rn(t, t, a[1][ni][1]);
-                        }
+                for (int ni = 0; ni < NI; ni++) {
+                    const double2 cc = *reinterpret_cast<const double2*>(cf + d * NB + cl + 8 * ni);
+                    double t;
+                    t = __dsub_rn(z0, cc.x); a[0][ni][0] = __fma_rn(t, t, a[0][ni][0]);
+                    t = __dsub_rn(z0, cc.y); a[0][ni][1] = __fma_rn(t, t, a[0][ni][1]);
+                    if (!ONE_ROW) {
+                        t = __dsub_rn(z1, cc.x); a[1][ni][0] = __fma_rn(t, t, a[1][ni][0]);
+                        t = __dsub_rn(z1, cc.y); a[1][ni][1] = __fma_rn(t, t, a[1][ni][1]);
                     }
                 }
             }

@@ -9,7 +9,7 @@ namespace gpslc {
 int ensure_workspace(Ctx* ctx, int NRB, int NCB, long long tasks, int* grid_out, int team, int split) {
     const size_t need = scratch_doubles(NRB, NCB) - row_off(split);
     const size_t needz = (size_t)2 * MAXRHS * NCB * NB;
-    if (ctx->slots == 0) ctx->slots = 2 * ctx->num_sms;   // upper bound on the grid of any factor kernel (sizes per-slot side buffers)
+    if (ctx->slots == 0) ctx->slots = CTAS_PER_SM * ctx->num_sms;   // upper bound on the grid of any factor kernel (sizes per-slot side buffers)
     // Resident factor CTAs per SM for this launch: two, so that one CTA's serial phases overlap the other's tensor work - except
     // for few large tasks (measured: 32 chains at n = 8192 run at 0.80 of peak with one CTA per SM and 0.42 with two, because the
     // second wave is nearly empty and every task runs at half speed; n = 2048, 64 chains: two CTAs 0.75, one 0.73; n = 4096, 64
@@ -20,8 +20,8 @@ int ensure_workspace(Ctx* ctx, int NRB, int NCB, long long tasks, int* grid_out,
     // members that share an SM, so large-matrix teams get an SM per CTA.
     int per = (e && atoi(e) > 0) ? atoi(e)
               : ((team == 1 && ((NCB >= 32 && tasks <= 3LL * ctx->num_sms) || (NCB >= 64 && tasks <= 6LL * ctx->num_sms))) ? 1
-                 : (team > 1 && NCB >= 32) ? 1 : 2);
-    if (per > 2) per = 2;
+                 : (team > 1 && NCB >= 32) ? 1 : CTAS_PER_SM);
+    if (per > CTAS_PER_SM) per = CTAS_PER_SM;
     // team > 1: one L scratch per team (cluster), one z buffer per CTA; *grid_out is the number of teams
     const long long max_slots = (long long)per * ctx->num_sms / team;
     long long grid = tasks < max_slots ? tasks : max_slots;
@@ -73,7 +73,7 @@ int ensure_zbuf(Ctx* ctx, int NCB, long long ctas) {
 int pick_team(Ctx* ctx, long long tasks, int NCB) {
     if (const char* e = getenv("GPSLC_TEAM")) { const int g = atoi(e); if (g == 1 || g == 2 || g == 4 || g == 8) return g; }
     // large matrices (>= 32 panels): one CTA per SM (see ensure_workspace), so the team size is chosen against the SM count
-    const long long resident = (NCB >= 32 ? 1LL : 2LL) * ctx->num_sms;
+    const long long resident = (NCB >= 32 ? 1LL : (long long)CTAS_PER_SM) * ctx->num_sms;
     int g = 1;
     if (NCB < 8) return 1;   // below n = 512 the redundant diagonal work and the cluster barriers eat the gain
     while (g < 8 && tasks * (2 * g) <= resident && 2 * g <= NCB) g *= 2;   // SMs would idle otherwise: larger teams win even at
@@ -280,7 +280,7 @@ int launch_cov_build(Ctx* ctx, int n, int batch, int D, const double* f1, const 
 struct LogpdfJobDense { const double* K; const double* y; int n; int ld; };
 
 template <bool FUSED>
-__global__ void __launch_bounds__(FTHREADS, 2)
+__global__ void __launch_bounds__(FTHREADS, CTAS_PER_SM)
 batched_logpdf_kernel(int batch, int n, const double* __restrict__ Kall, int ld, const double* __restrict__ yall, int y_shared,
                       // fused build inputs
                       int D, const double* __restrict__ feat, size_t feat_stride, const double* __restrict__ w,

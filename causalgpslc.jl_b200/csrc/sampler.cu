@@ -16,7 +16,8 @@ namespace gpslc {
 
 // ------------------------------------------------------------------------------------------------ device helpers
 
-__device__ __forceinline__ double ig_logpdf(double x, double shape, double scale) {
+// not inlined: log + lgamma at four call sites were 1500 instructions of the sampler kernels
+__device__ __noinline__ double ig_logpdf(double x, double shape, double scale) {
     if (!(x > 0.0)) return -INFINITY;
     return shape * log(scale) - lgamma(shape) - (shape + 1.0) * log(x) - scale / x;
 }
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(256) refresh_chains_kernel(ModelDev m, ChainDe
 }
 
 // L_S = chol(SigmaU) for a dense SigmaU, once per sampler (one CTA: a start-up cost, not part of any sweep)
-__global__ void __launch_bounds__(FTHREADS, 2) sigma_u_factor_kernel(const double* S, int n, double* SL, double* zbuf, int* info_out) {
+__global__ void __launch_bounds__(FTHREADS, CTAS_PER_SM) sigma_u_factor_kernel(const double* S, int n, double* SL, double* zbuf, int* info_out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FactorSmem& sm = *reinterpret_cast<FactorSmem*>(smem_raw);
     factor_smem_init(sm);
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(FTHREADS, 2) sigma_u_factor_kernel(const doubl
 // ------------------------------------------------------------------------------------------------ factor evaluation
 // tasks = (chain from list or all chains) x (existing factors); writes lp / lpP
 template <int TEAM>
-__global__ void __launch_bounds__(FTHREADS, 2)
+__global__ void __launch_bounds__(FTHREADS, CTAS_PER_SM)
 eval_factors_kernel(ModelDev m, ChainDev c, const int* list, const unsigned int* n_list_dev, int n_all, const int* exist,
                     int n_exist, int proposed, double* scratch, size_t slot_scratch, double* zbuf, size_t slot_z,
                     unsigned int* counter) {
@@ -293,7 +294,7 @@ eval_factors_kernel(ModelDev m, ChainDev c, const int* list, const unsigned int*
 // One task = (chain, lane): all single-site MH updates (src/proposal.jl:32-41 + Gen `mh`) of the
 // sites feeding one GP factor, for sweeps [j0, j1) of outer iteration `outer`.
 template <int TEAM>
-__global__ void __launch_bounds__(FTHREADS, 2)
+__global__ void __launch_bounds__(FTHREADS, CTAS_PER_SM)
 mh_lanes_kernel(ModelDev m, ChainDev c, const int* lane_order, int outer, int j0, int j1, double* scratch, size_t slot_scratch,
                 double* zbuf, size_t slot_z, unsigned int* counter) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -523,7 +524,7 @@ __device__ inline double block_bernoulli(const ModelDev& m, const double* Td, co
 // mode 1: once per outer iteration, factor the covariance of src/inference.jl:216-227 (per-dimension U vectors and the DATA X —
 //         not the model's effective U / X, App. B1/B3) and draw the nES slice directions nu_j = L z_j used by the logitT
 //         elliptical-slice updates of that iteration (App. B6: the covariance is NOT refreshed while U moves)
-__global__ void __launch_bounds__(FTHREADS, 2)
+__global__ void __launch_bounds__(FTHREADS, CTAS_PER_SM)
 logit_prior_kernel(ModelDev m, ChainDev c, int mode, int outer, double* scratch, size_t slot_scratch, double* zbuf, size_t slot_z,
                    double* xibuf, unsigned int* counter) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -583,7 +584,7 @@ logit_prior_kernel(ModelDev m, ChainDev c, int mode, int outer, double* scratch,
 // `elliptical_slice(trace, :logitT, zeros(n), logitTCov)` (src/inference.jl:233,293,347) for every chain: K_T is fixed during
 // the slice, so ONE factorisation with right-hand sides (f, nu) gives the quadratic form on the whole ellipse,
 // f'K^-1 f cos^2 + 2 f'K^-1 nu sin cos + nu'K^-1 nu sin^2; each shrink step then costs only the O(n) Bernoulli terms.
-__global__ void __launch_bounds__(FTHREADS, 2)
+__global__ void __launch_bounds__(FTHREADS, CTAS_PER_SM)
 ess_logit_kernel(ModelDev m, ChainDev c, int jj, uint32_t it, double* scratch, size_t slot_scratch, double* zbuf, size_t slot_z,
                  unsigned int* counter) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -936,6 +937,7 @@ template <class K1, class KT, class... Args>
 static int launch_single_or_team(Ctx* ctx, K1 k_single, KT k_team, int team, int grid, const char* what, Args... args) {
     if (team == 1) {
         GP_CUDA(ctx, cudaFuncSetAttribute(k_single, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FactorSmem)));
+        GP_CUDA(ctx, cudaFuncSetAttribute(k_single, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         k_single<<<grid, FTHREADS, sizeof(FactorSmem), ctx->stream>>>(args...);
         ctx->launches++;
         GP_CUDA(ctx, cudaGetLastError());
