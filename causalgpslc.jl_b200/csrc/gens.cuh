@@ -88,6 +88,7 @@ struct RbfGen {
     __device__ __noinline__ double one(int r, int c) const {
         if (r >= s->n || c >= s->n) return (r == c) ? 1.0 : 0.0;
         double a = 0.0;
+#pragma unroll 1
         for (int d = 0; d < s->D; d++) {
             const double* p = s->feat[d];
             const double w = s->sw[d];
@@ -149,11 +150,17 @@ struct RbfGen {
                 }
             }
         } else {
+            // slow path, kept small: a rolled loop over the entries through a local array (dynamic indexing is fine here)
+            double tmp[2 * NI * 2];
+#pragma unroll 1
+            for (int idx = 0; idx < (ONE_ROW ? 2 : 4) * NI; idx++) {
+                const int rr = idx / (2 * NI), ni = (idx >> 1) % NI, e = idx & 1;
+                tmp[idx] = one(rr ? r1 : r0, c0 + 8 * ni + e);
+            }
 #pragma unroll
             for (int ni = 0; ni < NI; ni++) {
-                const int c = c0 + 8 * ni;
-                v[0][ni][0] = one(r0, c); v[0][ni][1] = one(r0, c + 1);
-                if (!ONE_ROW) { v[1][ni][0] = one(r1, c); v[1][ni][1] = one(r1, c + 1); }
+                v[0][ni][0] = tmp[2 * ni]; v[0][ni][1] = tmp[2 * ni + 1];
+                if (!ONE_ROW) { v[1][ni][0] = tmp[2 * NI + 2 * ni]; v[1][ni][1] = tmp[2 * NI + 2 * ni + 1]; }
             }
         }
     }
