@@ -1,5 +1,5 @@
-"""Small invocations of the code paths added in round 2, meant to run under `compute-sanitizer --tool memcheck` (one tool per gpurun
-call): shared-Kp ITE (one CTA per task, cluster teams, grid-wide base factor), fused ITE summary, dense SigmaU sampler, radix-select
+"""Small invocations of the code paths added in round 2 (compute-sanitizer is closed on this pool, so this is a plain smoke run with
+finiteness / symmetry checks; written so that it can run under `compute-sanitizer --tool memcheck` where that is allowed): shared-Kp ITE (one CTA per task, cluster teams, grid-wide base factor), fused ITE summary, dense SigmaU sampler, radix-select
 summaries, 256-bit covariance stores with ragged n, many feature dimensions."""
 import os, sys
 import numpy as np
