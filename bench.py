@@ -166,6 +166,22 @@ def cpu_variants(budget_s=22.0):
     return out
 
 
+def cpu_c1():
+    """BASELINE configs[0] on the host: the oracle port's Posterior (24 / 10 / 5, one chain, incremental cost model — the reference's
+    own full re-score costs 3x that at this shape) on NEEC_sampled.csv plus the line-by-line ITE distributions at doT = 0.6."""
+    from oracle import data as od, inference as oi, estimation as oe
+    path = os.path.join(ROOT, "tests", "golden", "data", "NEEC_sampled.csv")
+    if not os.path.exists(path):
+        return None
+    t = time.perf_counter()
+    counts, obj, X, T, Y = od.prepare_data(path)
+    md = od.model_data_from_arrays(counts, X, T, Y, nU=1)
+    smp, _ = oi.posterior(md, 24, 10, 5, seed=2, chain=0, mode="incremental")
+    M, Cv = oe.ite_distributions(md.spec, smp, X, T, Y, 0.6, 10, 1, 1e-10)
+    oe.ite_samples(M, Cv, 10, seed=2)
+    return time.perf_counter() - t
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -375,6 +391,22 @@ def run_ours(args):
             extra[name] = {"value": world * C2 * st2 / (msx * 1e-3), "unit": "sweeps/s", "ms_per_step": msx / st2, "steps": st2, "warmup": wu2,
                            "tflops_per_gpu": tf, "frac": tf / peak,
                            "workload": f"n={n2}, {nobj2} objects, nX={nX2}, nU=1, {C2} chains per GPU, {Sx} sites per sweep"}
+        if rank == 0:
+            # c1, the reference's own use case (BASELINE configs[0]): gpslc(NEEC_sampled.csv) with default HyperParameters, ONE chain,
+            # then sampleITE(g, 0.6) and summarizeEstimates, end to end through the host mirror of the public API (CSV parsing included)
+            neec = os.path.join(ROOT, "tests", "golden", "data", "NEEC_sampled.csv")
+            if os.path.exists(neec):
+                g.gpslc(neec, seed=1, ctx=ctx)                      # warm-up (workspace sizes of this shape)
+                ctx.synchronize()
+                tc1 = time.perf_counter()
+                gobj = g.gpslc(neec, seed=2, ctx=ctx)
+                tfit = time.perf_counter() - tc1
+                itec1 = g.sampleITE(gobj, 0.6, ctx=ctx)
+                g.summarizeEstimates(itec1, ctx=ctx)
+                tc1 = time.perf_counter() - tc1
+                extra["c1"] = {"seconds": tc1, "gpslc_seconds": tfit, "mh_sweeps_per_s": 240.0 / tfit, "ite_samples": int(itec1.shape[1]),
+                               "workload": "gpslc(NEEC_sampled.csv: n=150, 6 objects, no covariates) with default HyperParameters (24 outer x (10 MH "
+                                           "sweeps + 5 slice passes)), 1 chain, + sampleITE(g, 0.6) + summarizeEstimates"}
         if world == 8 or os.environ.get("GPSLC_BENCH_C5"):       # the env switch runs a proportional share (32 doT per GPU) at any N
             extra["c5"] = run_c5(g, ge, ctx, rank, world, pri, peak, barrier, max_over_ranks, n_dot=32 * world)
 
@@ -404,6 +436,7 @@ def run_ours(args):
         # ---- CPU baseline on the box's host cores (bounded samples, rank 0 at N=1 only)
         if world == 1 and not args.no_cpu:
             v = cpu_variants()
+            v["c1_seconds"] = cpu_c1()
             fa = v["faithful_all_cores"]
             line["cpu_baseline"] = {"value": fa["value"], "unit": "sweeps/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"{fa['sites_timed']} of 58 single-site MH updates of one sweep of one chain at the c3 shape, "
