@@ -324,7 +324,8 @@ int launch_sate(Ctx*, const EstArgs&);
 static int est_common(gpslc_ctx* h, int loc, const gpslc_data* d, const double* samples, int n_outer, int n_chains, int stride,
                       const int* ret_idx, int R, const double* doT, int n_doT, double jitter, int spp, uint64_t seed,
                       int chain_offset, int var_as_std, bool sate, double* o1, double* o2, double* o3, int* info, int dot_offset = 0,
-                      double summary_ci = 0.0, double* summary = nullptr) {
+                      double summary_ci = 0.0, double* summary = nullptr, const unsigned char* subset_mask = nullptr,
+                      double* subset_sate = nullptr) {
     if (!h) return GPSLC_ERR_ARG;
     Ctx* ctx = &h->c;
     if (!d || !samples || !ret_idx || !doT || d->n <= 0 || R < 0 || n_doT < 0 || n_chains <= 0 || spp < 0)
@@ -357,16 +358,35 @@ static int est_common(gpslc_ctx* h, int loc, const gpslc_data* d, const double* 
     GP_TRY(dInfo.outbuf(loc, info, tasks));
     a.info = dInfo.d;
     int rc;
-    Staged<double> dSum(ctx);
+    Staged<double> dSum(ctx), dSub(ctx);
     if (!sate && summary) {
         // fused predictCounterfactualEffects + summarizeEstimates: the draws live only in the library's device arena
         if (spp <= 0) return ctx->fail(GPSLC_ERR_ARG, "gpslc_ite_summary: samplesPerPosterior must be positive");
         double* draws = nullptr;
         GP_CUDA(ctx, ctx->arena_alloc(reinterpret_cast<void**>(&draws), tasks * spp * n * sizeof(double)));
-        GP_TRY(dSum.outbuf(loc, summary, (size_t)n_doT * n_chains * n * 3));
         a.mean_out = nullptr; a.cov_out = nullptr; a.ite_out = draws;
-        rc = launch_ite(ctx, a);
-        if (!rc) rc = launch_summarize(ctx, draws, n_doT * n_chains, R * spp, n, summary_ci, dSum.d);
+        if (!subset_mask) {
+            GP_TRY(dSum.outbuf(loc, summary, (size_t)n_doT * n_chains * n * 3));
+            rc = launch_ite(ctx, a);
+            if (!rc) rc = launch_summarize(ctx, draws, n_doT * n_chains, R * spp, n, summary_ci, dSum.d);
+        } else {
+            // subgroup effect curve (docs/src/index.md:101-114): draws -> mean over the subset -> per (chain, doT) summary; the mask
+            // is a small host array in either mode
+            int cnt = 0;
+            for (int i = 0; i < n; i++) cnt += subset_mask[i] != 0;
+            if (cnt == 0) return ctx->fail(GPSLC_ERR_ARG, "gpslc_ite_subset_summary: the subset is empty");
+            Staged<unsigned char> dMask(ctx);
+            GP_TRY(dMask.in(0, subset_mask, n));
+            const size_t nsub = (size_t)n_chains * R * spp * n_doT;
+            GP_TRY(dSub.outbuf(loc, subset_sate, nsub));
+            double* sub = dSub.d;
+            if (!sub) GP_CUDA(ctx, ctx->arena_alloc(reinterpret_cast<void**>(&sub), nsub * sizeof(double)));
+            GP_TRY(dSum.outbuf(loc, summary, (size_t)n_chains * n_doT * 3));
+            rc = launch_ite(ctx, a);
+            if (!rc) rc = launch_subset_mean(ctx, draws, dMask.d, tasks * spp, R * spp, n, n_chains, n_doT, cnt, sub);
+            if (!rc) rc = launch_summarize(ctx, sub, n_chains, R * spp, n_doT, summary_ci, dSum.d);
+            if (!rc) rc = dSub.finish();
+        }
         if (!rc) rc = dSum.finish();
     } else if (!sate) {
         GP_TRY(d1.outbuf(loc, o1, tasks * n));
@@ -407,6 +427,34 @@ int gpslc_ite_summary(gpslc_ctx* h, int loc, const gpslc_data* d, const double* 
     if (dot_offset < 0 || !summary || !(credible_interval > 0.0 && credible_interval < 1.0)) return GPSLC_ERR_ARG;
     return est_common(h, loc, d, samples, n_outer, n_chains, stride, ret_idx, R, doT, n_doT, jitter, spp, seed, chain_offset, 0,
                       false, nullptr, nullptr, nullptr, info, dot_offset, credible_interval, summary);
+}
+int gpslc_ite_subset_summary(gpslc_ctx* h, int loc, const gpslc_data* d, const double* samples, int n_outer, int n_chains, int stride,
+                             const int* ret_idx, int R, const double* doT, int n_doT, int dot_offset, double jitter, int spp,
+                             uint64_t seed, int chain_offset, const unsigned char* mask, double credible_interval, double* sate,
+                             double* summary, int* info) {
+    if (dot_offset < 0 || !summary || !mask || !(credible_interval > 0.0 && credible_interval < 1.0)) return GPSLC_ERR_ARG;
+    return est_common(h, loc, d, samples, n_outer, n_chains, stride, ret_idx, R, doT, n_doT, jitter, spp, seed, chain_offset, 0,
+                      false, nullptr, nullptr, nullptr, info, dot_offset, credible_interval, summary, mask, sate);
+}
+int gpslc_subset_mean(gpslc_ctx* h, int loc, const double* samples, int batch, int m, int n, const unsigned char* mask, double* out) {
+    if (!h) return GPSLC_ERR_ARG;
+    Ctx* ctx = &h->c;
+    if (!samples || !out || !mask || batch < 0 || m <= 0 || n <= 0) return ctx->fail(GPSLC_ERR_ARG, "gpslc_subset_mean: bad argument");
+    int cnt = 0;
+    for (int i = 0; i < n; i++) cnt += mask[i] != 0;
+    if (cnt == 0) return ctx->fail(GPSLC_ERR_ARG, "gpslc_subset_mean: the subset is empty");
+    if (batch == 0) return GPSLC_OK;
+    GP_CUDA(ctx, cudaSetDevice(ctx->device));
+    ArenaScope arena_scope(ctx);
+    Staged<double> dS(ctx), dO(ctx);
+    Staged<unsigned char> dM(ctx);
+    GP_TRY(dS.in(loc, samples, (size_t)batch * m * n));
+    GP_TRY(dM.in(0, mask, n));
+    GP_TRY(dO.outbuf(loc, out, (size_t)batch * m));
+    GP_TRY(launch_subset_mean(ctx, dS.d, dM.d, (size_t)batch * m, m, n, 0, 0, cnt, dO.d));
+    GP_TRY(dO.finish());
+    GP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GPSLC_OK;
 }
 int gpslc_sate_slice(gpslc_ctx* h, int loc, const gpslc_data* d, const double* samples, int n_outer, int n_chains, int stride,
                      const int* ret_idx, int R, const double* doT, int n_doT, int dot_offset, double jitter, int spp, uint64_t seed,

@@ -32,5 +32,7 @@ struct EstArgs {
 
 struct Ctx;
 int launch_summarize(Ctx* ctx, const double* samples, int batch, int m, int n, double ci, double* out);
+int launch_subset_mean(Ctx* ctx, const double* samples, const unsigned char* mask, size_t rows, int m, int n, int groups, int n_d,
+                       int count, double* out);
 
 }  // namespace gpslc

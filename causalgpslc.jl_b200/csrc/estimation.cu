@@ -718,6 +718,44 @@ __global__ void __launch_bounds__(256) summarize_select_kernel(const double* __r
     }
 }
 
+// Subgroup average of the docs example (docs/src/index.md:101-108: `mean(ite[:, maIdx, :], dims = 2)`): one warp per row
+// (batch element b, draw s) of samples [batch][m][n] sums the masked individuals — coalesced, every sample read once (HBM-bound,
+// 8 n bytes per row), fixed summation order (lane-strided partial sums, then a shuffle tree). groups > 0 transposes the result for the
+// summary that follows: b = d * groups + c goes to out[c][s][d] (per chain the column-major nDoT x nSamples matrix the docs example
+// hands to summarizeEstimates); groups == 0: out[b][s].
+__global__ void __launch_bounds__(256) subset_mean_kernel(const double* __restrict__ samples, const unsigned char* __restrict__ mask,
+                                                          size_t rows, int m, int n, int groups, int n_d, double inv_count,
+                                                          double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const size_t wpg = (size_t)gridDim.x * (blockDim.x >> 5);
+    for (size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += wpg) {
+        const double* src = samples + row * n;
+        double sum = 0.0;
+        for (int i = lane; i < n; i += 32)
+            if (mask[i]) sum += src[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) {
+            size_t oi = row;
+            if (groups > 0) {
+                const size_t b = row / m, s = row - b * m, d = b / groups, c = b - d * groups;
+                oi = (c * m + s) * n_d + d;
+            }
+            out[oi] = sum * inv_count;
+        }
+    }
+}
+
+int launch_subset_mean(Ctx* ctx, const double* samples, const unsigned char* mask, size_t rows, int m, int n, int groups, int n_d,
+                       int count, double* out) {
+    const size_t want = (rows + 7) / 8;
+    const int grid = (int)(want < (size_t)(148 * 8) ? want : (size_t)(148 * 8));
+    subset_mean_kernel<<<grid, 256, 0, ctx->stream>>>(samples, mask, rows, m, n, groups, n_d, 1.0 / count, out);
+    ctx->launches++;
+    GP_CUDA(ctx, cudaGetLastError());
+    return GPSLC_OK;
+}
+
 int launch_summarize(Ctx* ctx, const double* samples, int batch, int m, int n, double ci, double* out) {
     int mpad = 2;
     while (mpad < m) mpad <<= 1;

@@ -11,5 +11,5 @@ from .data import prepareData, objectCounts  # noqa: F401
 from .inference import Posterior, ChainSampler  # noqa: F401
 from .driver import (gpslc, samplePosterior, sampleITE, sampleSATE, summarizeEstimates, ITEDistributions,  # noqa: F401
                      SATEDistributions)
-from .prediction import predictCounterfactualEffects  # noqa: F401
+from .prediction import predictCounterfactualEffects, subgroupEffectCurve  # noqa: F401
 from .io import saveGPSLCObject, loadGPSLCObject  # noqa: F401

@@ -30,6 +30,10 @@ def _bind_est(lib):
     lib.gpslc_ite_summary.argtypes = [vp, i, P(GpslcData), vp, i, i, i, vp, i, vp, i, i, dbl, i, u64, i, dbl, vp, vp]
     lib.gpslc_summarize.restype = i
     lib.gpslc_summarize.argtypes = [vp, i, vp, i, i, i, dbl, vp]
+    lib.gpslc_ite_subset_summary.restype = i
+    lib.gpslc_ite_subset_summary.argtypes = [vp, i, P(GpslcData), vp, i, i, i, vp, i, vp, i, i, dbl, i, u64, i, vp, dbl, vp, vp, vp]
+    lib.gpslc_subset_mean.restype = i
+    lib.gpslc_subset_mean.argtypes = [vp, i, vp, i, i, i, vp, vp]
     lib._est_bound = True
 
 
@@ -102,6 +106,46 @@ def ite_summary(samples, X, T, Y, nU, doT, ret_idx, jitter, spp, seed=0, chain_o
                                         int(dot_offset), float(jitter), int(spp), int(seed), int(chain_offset),
                                         float(credible_interval), ptr(out), ptr(info)))
     return out, info
+
+
+def ite_subset_summary(samples, X, T, Y, nU, doT, ret_idx, jitter, spp, mask, seed=0, chain_offset=0, credible_interval=0.90, ctx=None,
+                       dot_offset=0):
+    """gpslc_ite_subset_summary — the subgroup workflow of docs/src/index.md:101-114 fused on the device: the ITE draws of every doT
+    are averaged over the individuals selected by `mask` and summarised over the draws. Returns (summary [C, D, 3] = Mean / LowerBound /
+    UpperBound per doT, sate [C, R*spp, D], info [D, C, R])."""
+    from .kernel import default_context
+    ctx = ctx or default_context()
+    _bind(ctx.lib); _bind_est(ctx.lib)
+    samples = np.ascontiguousarray(samples, dtype=np.float64)
+    n_outer, C, stride = samples.shape
+    d, keep = _data_struct(X, T, Y, nU)
+    doT = np.ascontiguousarray(np.atleast_1d(np.asarray(doT, dtype=np.float64)))
+    ret = np.ascontiguousarray(ret_idx, dtype=np.int32)
+    D, R, n = doT.shape[0], ret.shape[0], d.n
+    mask = np.ascontiguousarray(np.asarray(mask).astype(bool), dtype=np.uint8)
+    if mask.shape != (n,):
+        raise ValueError("mask must have one entry per individual")
+    out = np.empty((C, D, 3)); sub = np.empty((C, R * spp, D))
+    info = np.empty((D, C, R), dtype=np.int32)
+    ctx.check(ctx.lib.gpslc_ite_subset_summary(ctx.h, HOST, ctypes.byref(d), ptr(samples), n_outer, C, stride, ptr(ret), R, ptr(doT), D,
+                                               int(dot_offset), float(jitter), int(spp), int(seed), int(chain_offset), ptr(mask),
+                                               float(credible_interval), ptr(sub), ptr(out), ptr(info)))
+    return out, sub, info
+
+
+def subset_mean(samples, mask, ctx=None):
+    """gpslc_subset_mean: `mean(ite[:, idx, :], dims=2)` for samples [batch, m, n] (the layout gpslc_ite writes) -> [batch, m]."""
+    from .kernel import default_context
+    ctx = ctx or default_context()
+    _bind(ctx.lib); _bind_est(ctx.lib)
+    samples = np.ascontiguousarray(samples, dtype=np.float64)
+    B, m, n = samples.shape
+    mask = np.ascontiguousarray(np.asarray(mask).astype(bool), dtype=np.uint8)
+    if mask.shape != (n,):
+        raise ValueError("mask must have one entry per individual")
+    out = np.empty((B, m))
+    ctx.check(ctx.lib.gpslc_subset_mean(ctx.h, HOST, ptr(samples), B, m, n, ptr(mask), ptr(out)))
+    return out
 
 
 def sate(samples, X, T, Y, nU, doT, ret_idx, jitter, spp, seed=0, chain_offset=0, var_as_std=True, ctx=None, dot_offset=0):

@@ -287,6 +287,38 @@ function predictCounterfactualSummaryShard(g, nSamplesPerMixture::Int, world_siz
 end
 
 """
+    subgroupEffectCurveShard(g, idx, nSamplesPerMixture, world_size, rank; fidelity=100, minDoT, maxDoT, credible_interval=0.90)
+The documented subgroup workflow (docs/src/index.md:101-114) fused on the device through gpslc_ite_subset_summary:
+`ite, doT = predictCounterfactualEffects(g, nSamples); sate = mean(ite[:, idx, :], dims=2)[:, 1, :]; summarizeEstimates(sate)`.
+`idx` is a Bool vector over the individuals (e.g. `vec(g.obj .== "MA")`). Returns (summary, sate, doTrange, offset) for this rank's
+block of doT values: `summary[3, d_local]` = (Mean, LowerBound, UpperBound) per doT, `sate[d_local, R*nSamplesPerMixture]`.
+"""
+function subgroupEffectCurveShard(g, idx::AbstractVector{Bool}, nSamplesPerMixture::Int, world_size::Int, rank::Int; fidelity::Int=100,
+                                  minDoT=min(g.T...), maxDoT=max(g.T...), seed=UInt64(0), credible_interval::Float64=0.90)
+    doTrange = minDoT:(abs(maxDoT - minDoT) / fidelity):maxDoT
+    all = collect(Float64, doTrange); D = length(all)
+    base, rem = divrem(D, world_size)
+    cnt = base + (rank < rem ? 1 : 0); off = rank * base + min(rank, rem)
+    dts = all[off+1:off+cnt]
+    packed = pack(g); ret = retained(g.hyperparams); R = length(ret); n = length(g.Y)
+    length(idx) == n || throw(ArgumentError("idx must have one entry per individual"))
+    mask = UInt8.(idx)
+    Tf = Float64.(g.T); Xf = g.X === nothing ? Float64[] : Matrix{Float64}(g.X); Yf = Float64.(g.Y)
+    out = Array{Float64}(undef, 3, cnt)                              # C layout [1][d_local][3]
+    sate = Array{Float64}(undef, cnt, R * nSamplesPerMixture)        # C layout [1][R*spp][d_local]
+    info = zeros(Cint, R * cnt)
+    GC.@preserve packed ret Tf Xf Yf out sate dts info mask begin
+        check(ccall((:gpslc_ite_subset_summary, LIB[]), Cint,
+                    (Ptr{Cvoid}, Cint, Ref{GpslcData}, Ptr{Cdouble}, Cint, Cint, Cint, Ptr{Cint}, Cint, Ptr{Cdouble}, Cint, Cint, Cdouble,
+                     Cint, UInt64, Cint, Ptr{UInt8}, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cint}),
+                    CTX[], 0, data_struct(g, Tf, Xf, Yf), packed, size(packed, 3), 1, size(packed, 1), ret, R, dts, cnt, off,
+                    g.hyperparams.predictionCovarianceNoise, nSamplesPerMixture, seed, 0, mask, credible_interval, sate, out, info))
+    end
+    check_info(info)
+    out, sate, doTrange, off
+end
+
+"""
     summarizeEstimates(samples; credible_interval=0.90) — the statistics of src/driver.jl:129-149 (row mean and the two
 quantiles, Julia `quantile` default) through gpslc_summarize. `samples` is the n × m matrix sampleITE returns, whose memory
 is exactly the C layout [m][n]. Returns (Mean, LowerBound, UpperBound) vectors; the DataFrame/CSV part stays in driver.jl.

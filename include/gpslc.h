@@ -219,6 +219,23 @@ int gpslc_ite_summary(gpslc_ctx* ctx, int loc, const gpslc_data* data, const dou
                       const int* ret_idx, int R, const double* doT, int n_doT, int dot_offset, double jitter, int spp, uint64_t seed,
                       int chain_offset, double credible_interval, double* summary, int* info);
 
+/* The subgroup effect curve of the reference's documented workflow (docs/src/index.md:101-114):
+ *   ite, doT = predictCounterfactualEffects(g, nSamples); sate = mean(ite[:, idx, :], dims=2)[:, 1, :]; summarizeEstimates(sate)
+ * in one call; the draws and the subgroup averages are produced and reduced in HBM.
+ *   mask    [n] bytes (host memory in either mode), non-zero = the individual belongs to the subgroup; at least one
+ *   sate    [n_chains][R*spp][n_doT]  subgroup average of every draw — per chain the column-major nDoT x nSamples matrix the
+ *                                     example hands to summarizeEstimates (may be NULL)
+ *   summary [n_chains][n_doT][3]      Mean, LowerBound, UpperBound over the R*spp draws, one row per doT value
+ * doT / dot_offset / info as in gpslc_ite_slice (a shard covers a contiguous block of doT values). */
+int gpslc_ite_subset_summary(gpslc_ctx* ctx, int loc, const gpslc_data* data, const double* samples, int n_outer, int n_chains,
+                             int stride, const int* ret_idx, int R, const double* doT, int n_doT, int dot_offset, double jitter,
+                             int spp, uint64_t seed, int chain_offset, const unsigned char* mask, double credible_interval,
+                             double* sate, double* summary, int* info);
+/* mean(samples[:, idx, :], dims=2) alone (docs/src/index.md:104-108): samples [batch][m][n] (the layout gpslc_ite writes) ->
+ * out [batch][m]; HBM-bound, every sample read once. */
+int gpslc_subset_mean(gpslc_ctx* ctx, int loc, const double* samples, int batch, int m, int n, const unsigned char* mask,
+                      double* out);
+
 /* summarizeEstimates (src/driver.jl:129-149): for every individual the mean and the (1-ci)/2 and 1-(1-ci)/2 quantiles of its
  * m samples, Julia's default `quantile` (linear interpolation between order statistics, type 7; KAT test/driver.jl:54-71).
  *   samples [batch][m][n]  — the layout gpslc_ite writes (`ite` for one doT and one chain is one batch element with

@@ -811,6 +811,39 @@ def test_counterfactual_sweep_shards_concatenate(ctx):
         assert np.array_equal(np.concatenate(parts, axis=0), whole)
 
 
+def test_subgroup_effect_curve_matches_the_documented_workflow(ctx):
+    """docs/src/index.md:101-114 on the example data: `ite, doT = predictCounterfactualEffects(g, nSamples)`, `maITE = ite[:, maIdx, :]`,
+    `sate = mean(maITE, dims=2)[:, 1, :]`, `summarizeEstimates(sate)`. The fused device path (gpslc_ite_subset_summary) must equal the
+    unfused host arithmetic on the SAME draws (the sweep's draws are keyed by the global doT index): subgroup averages to 1e-12,
+    the summary to the quantile KAT's tolerance; shards concatenate; gpslc_subset_mean alone agrees as well."""
+    path = os.path.join(GOLD, "data", "NEEC_sampled.csv")
+    h = g.getHyperParameters(); h.nOuter, h.nBurnIn = 8, 3
+    gobj = g.gpslc(path, hyperparams=h, seed=5, ctx=ctx)
+    idx = np.asarray(gobj.obj) == "MA"                                          # the example's `vec(g.obj .== "MA")`
+    assert 0 < idx.sum() < len(idx)
+    ite, rng_ = g.predictCounterfactualEffects(gobj, 7, fidelity=9, ctx=ctx)    # [d, n, R*7]
+    want_sate = ite[:, idx, :].mean(axis=1)                                     # [d, m]
+    interval, sate, rng2 = g.subgroupEffectCurve(gobj, idx, 7, fidelity=9, ctx=ctx)
+    assert np.array_equal(rng_, rng2) and sate.shape == want_sate.shape
+    assert np.max(np.abs(sate - want_sate)) <= 1e-12 * max(1.0, np.abs(want_sate).max())
+    lo, hi = np.quantile(want_sate, [0.05, 0.95], axis=1)
+    assert np.allclose(interval["Mean"], want_sate.mean(axis=1), rtol=1e-12, atol=1e-13)
+    assert np.allclose(interval["LowerBound"], lo, rtol=1e-12, atol=1e-13) and np.allclose(interval["UpperBound"], hi, rtol=1e-12, atol=1e-13)
+    # the same table through the unfused public calls
+    tab = g.summarizeEstimates(want_sate, ctx=ctx)
+    assert np.allclose(tab["Mean"], interval["Mean"], rtol=1e-12, atol=1e-13) and np.allclose(tab["UpperBound"], interval["UpperBound"], rtol=1e-12, atol=1e-13)
+    # doT shards (BASELINE c5 layout) concatenate to the whole curve
+    parts = [g.subgroupEffectCurve(gobj, idx, 7, fidelity=9, ctx=ctx, world_size=3, rank=r) for r in range(3)]
+    assert np.array_equal(np.concatenate([p[1] for p in parts], axis=0), sate)
+    assert np.array_equal(np.concatenate([p[0]["LowerBound"] for p in parts]), interval["LowerBound"])
+    # stand-alone subgroup mean on the gpslc_ite layout [batch][m][n]
+    from gpslc_b200 import estimation as ge_
+    lay = np.ascontiguousarray(np.swapaxes(ite, 1, 2))
+    assert np.max(np.abs(ge_.subset_mean(lay, idx, ctx=ctx) - want_sate)) <= 1e-12 * max(1.0, np.abs(want_sate).max())
+    with pytest.raises(Exception):
+        ge_.subset_mean(lay, np.zeros(len(idx), bool), ctx=ctx)                 # empty subgroup is an argument error
+
+
 def test_binary_treatment_end_to_end_ihdp(ctx):
     """IHDP_sampled.csv (n=272, 6 covariates, 200 objects, Bool T): gpslc -> sampleITE(true/false) -> summarizeEstimates through the
     public API runs the binary-T sampler (logitT slices); ONE default chain must pass the reference's own gate against the golden

@@ -140,7 +140,8 @@ _C2JL = {"int": {"Cint"}, "double": {"Cdouble"}, "uint64_t": {"UInt64"}, "size_t
          "const double*": {"Ptr{Cdouble}"}, "double*": {"Ptr{Cdouble}"}, "const int*": {"Ptr{Cint}"}, "int*": {"Ptr{Cint}"},
          "unsigned long long*": {"Ptr{Culonglong}"}, "gpslc_ctx*": {"Ptr{Cvoid}"}, "const gpslc_ctx*": {"Ptr{Cvoid}"},
          "gpslc_ctx**": {"Ref{Ptr{Cvoid}}"}, "const gpslc_data*": {"Ref{GpslcData}"}, "const gpslc_prior*": {"Ref{GpslcPrior}"},
-         "const gpslc_opts*": {"Ref{GpslcOpts}"}, "const char*": {"Cstring"}, "void": {"Cvoid"}}
+         "const gpslc_opts*": {"Ref{GpslcOpts}"}, "const char*": {"Cstring"}, "void": {"Cvoid"},
+         "const unsigned char*": {"Ptr{UInt8}"}}
 
 
 def _split_top(s):
