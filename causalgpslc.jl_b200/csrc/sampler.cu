@@ -277,7 +277,7 @@ eval_factors_kernel(ModelDev m, ChainDev c, const int* list, const unsigned int*
         build_spec(m, c, chain, f, Ubase, -1, 0.0, &spec);
         __syncthreads();
         RbfGen gen{&spec, sm.exp2tab};
-        factor_run<RbfGen, TEAM>(gen, NCB, NCB, 1, my_scratch, my_z, sm, pipe);
+        factor_run<RbfGen, TEAM>(gen, NCB, NCB, 1, my_scratch, my_z, sm, pipe, 1 << 30, nullptr, 0, nullptr, nullptr, 0, nullptr, /*keep_diag=*/false);
         if (threadIdx.x == 0 && trank == 0) {
             const FactorOut o = sm.out;
             (proposed ? c.lpP : c.lp)[(size_t)chain * m.nF + f] = logpdf_from(o, m.n);
@@ -368,7 +368,7 @@ mh_lanes_kernel(ModelDev m, ChainDev c, const int* lane_order, int outer, int j0
                     build_spec(m, c, chain, f, Ubase, sd.param, nw, &spec);
                     __syncthreads();
                     RbfGen gen{&spec, sm.exp2tab};
-                    factor_run<RbfGen, TEAM>(gen, NCB, NCB, 1, my_scratch, my_z, sm, pipe);
+                    factor_run<RbfGen, TEAM>(gen, NCB, NCB, 1, my_scratch, my_z, sm, pipe, 1 << 30, nullptr, 0, nullptr, nullptr, 0, nullptr, /*keep_diag=*/false);
                     dlik = 0.0;
                 } else {
                     __syncthreads();
