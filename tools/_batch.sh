@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
-timeout 800 python -m pytest tests -m gpu -q -x 2>&1 | tail -4
-python bench.py --gpus 1 --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_eg.json 2> gpurun_out/bench_eg.err
+( time python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench_n2_r02i.json 2> gpurun_out/bench_n2_r02i.err ) 2>&1 | tail -3
 python -c "
-import json; d=json.load(open('gpurun_out/bench_eg.json')); print(round(d['value'],1), round(d['roofline']['frac'],4), 'c2', round(d['c2']['value']), round(d['c2']['frac'],3), 'e2e', round(d['e2e']['value'],1), 'c1', d.get('c1',{}).get('seconds'), d.get('c1',{}).get('gpslc_seconds'))"
-for g in 1 2 4 8; do echo group $g; GPSLC_ESS_GROUP=$g python tools/gpu_ess_pass_time.py 256 4 5 1024 2>&1 | tail -1; GPSLC_ESS_GROUP=$g python tools/gpu_ess_pass_time.py 150 6 0 1 2>&1 | tail -1; GPSLC_ESS_GROUP=$g python tools/gpu_ess_pass_time.py 1024 16 10 512 2>&1 | tail -1; done
+import json; d=json.loads(open('gpurun_out/bench_n2_r02i.json').read().strip().splitlines()[-1]); print(d['n_gpus'], round(d['value'],1), round(d['roofline']['frac'],4), 'e2e', d['e2e']['value'], d['e2e'].get('gather_ms'), 'strong', d.get('strong'), 'c2', d['c2']['value'], 'c1', d.get('c1',{}).get('seconds'))"
+( time python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 3 --warmup 1 > gpurun_out/bench_ref_n2.json 2>/dev/null ) 2>&1 | tail -3; cut -c1-160 gpurun_out/bench_ref_n2.json
+tail -3 gpurun_out/bench_n2_r02i.err
