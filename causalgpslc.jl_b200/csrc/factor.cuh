@@ -53,7 +53,7 @@ constexpr int MAXRHS = 2;
 constexpr int CS_LD = 66;              // P2 workspace leading dimension (16-byte aligned rows)
 constexpr int CS_ROWS = 72;            // 64 matrix rows + up to MAXRHS right-hand-side rows + zero padding to a full 8-row tile
 constexpr int LINV_D = 72 * 32;        // atoms (n8, k4) with k4 <= 2*n8+1, row n8 starts at atom n8*(n8+1)
-constexpr int CF_DIMS = (GPSLC_CTAS >= 3) ? 4 : 24;   // feature dimensions staged per panel (more dimensions fall back to global loads)
+constexpr int CF_DIMS = (GPSLC_CTAS >= 3) ? 6 : 24;   // feature dimensions staged per panel (more dimensions fall back to global loads)
 
 struct FactorOut {
     double logdet;      // log det K
@@ -686,6 +686,9 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
             int srow[DSLOTS], scol[DSLOTS];
 #pragma unroll
             for (int sl = 0; sl < DSLOTS; sl++) diag_slot(warp, sl, srow[sl], scol[sl]);
+            // tile rows of the slots: warps 0-3 hold row pw in slots 0..pw and row 7-pw in the others, warps 4-7 row 7-pw only
+            const int rowA = (warp < 4) ? (warp & 3) : 7 - (warp & 3), rowB = 7 - (warp & 3);
+            const int splitA = (warp < 4) ? (warp & 3) : DSLOTS;
             double acc[DSLOTS][2];
 #pragma unroll
             for (int sl = 0; sl < DSLOTS; sl++) { acc[sl][0] = 0.0; acc[sl][1] = 0.0; }
@@ -735,10 +738,14 @@ __device__ void factor_run(const Gen& gen, const int NRB, const int NCB, const i
                         const double* sB = sm.stage + st * STAGE_D + SLAB_D + kk2 * SLAB_D;
 #pragma unroll
                         for (int k4 = 0; k4 < K4S; k4++) {
+                            // the slots of a warp lie in at most two tile rows (diag_slot): their A fragments are loaded once per
+                            // row, not once per tile - this loop is otherwise bound by the shared-memory pipe (two LDS.64 per DMMA)
+                            const double aA = sB[(rowA * K4S + k4) * 32 + lane];
+                            const double aB = (warp < 4) ? sB[(rowB * K4S + k4) * 32 + lane] : aA;
 #pragma unroll
                             for (int sl = 0; sl < DSLOTS; sl++) {
                                 if (sl < nslots) {
-                                    const double a = sB[(srow[sl] * K4S + k4) * 32 + lane];
+                                    const double a = (sl > splitA) ? aB : aA;
                                     const double b = sB[(scol[sl] * K4S + k4) * 32 + lane];
                                     dmma(acc[sl], a, b);
                                 }
