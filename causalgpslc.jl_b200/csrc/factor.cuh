@@ -50,7 +50,14 @@ constexpr int FWARPS = 8;
 constexpr int FTHREADS = FWARPS * 32;
 constexpr int STAGE_D = 3 * SLAB_D;    // A0 | A1 | B
 constexpr int MAXRHS = 2;
-constexpr int CS_LD = 66;              // P2 workspace leading dimension (16-byte aligned rows)
+// P2 workspace leading dimension (16-byte aligned rows). 68 = 4 mod 16 makes the A-fragment loads of P2 (LDS.64 at row g, column q)
+// conflict-free per half-warp; with 66 every shared-memory access of P2's update was a 2-way conflict (ncu source page, c2: 3.5e9 of
+// 20.6e9 wavefronts in excess). The 128-bit accumulator-layout accesses would want 8 mod 16 instead - no pitch serves both; measured
+// at n = 256 / 128: 68 +1.5 % / +2.9 %, 72 +1.1 % / +2.1 %, c3 +0.15 %.
+#ifndef GPSLC_CS_LD
+#define GPSLC_CS_LD 68
+#endif
+constexpr int CS_LD = GPSLC_CS_LD;
 constexpr int CS_ROWS = 72;            // 64 matrix rows + up to MAXRHS right-hand-side rows + zero padding to a full 8-row tile
 constexpr int LINV_D = 72 * 32;        // atoms (n8, k4) with k4 <= 2*n8+1, row n8 starts at atom n8*(n8+1)
 constexpr int CF_DIMS = (GPSLC_CTAS >= 3) ? 6 : 24;   // feature dimensions staged per panel (more dimensions fall back to global loads)
