@@ -2,7 +2,8 @@
 """Benchmark of the GP-SLC hot path on B200 (BASELINE.json metric: MH sweeps/sec summed over chains at n=1024).
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-  python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores (oracle port)
+  python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores (oracle port): one chain of the
+                                                           # workload per core, one BLAS thread each, sweeps/s summed over them
 
 One "step" = one Metropolis-Hastings sweep (the body of `for j = 1:nMHInner`, /root/reference/src/inference.jl:22-45:
 S = 6 + nU(2+nX) + 4nX = 58 single-site updates) of EVERY chain on the rank: config c3 of BASELINE.json — synthetic
@@ -15,7 +16,8 @@ Keys beyond the contract:
            chain; at N > 1 the packed samples are gathered over NCCL (device buffers) inside the timed region.
   c2, c4   the other single-GPU BASELINE configurations (sweeps/s and fraction of the FP64 peak); c5 when N == 8.
   strong   (N > 1) the same kernel with 512 chains TOTAL, i.e. 512/N per GPU.
-  cpu_baseline.variants  the oracle port in the reference's cost model (all cores / one BLAS thread) and incrementally.
+  cpu_baseline           the oracle port in the reference's cost model, as many chains of the workload as host cores (one process and
+                         one BLAS thread per chain); .variants: ONE chain with all cores / one BLAS thread, and the incremental cost model.
 """
 import argparse
 import json
@@ -119,8 +121,18 @@ def ncu_traffic():
     return None
 
 
+def bench_config(S=58):
+    """The `config` object of both arms (ours and --impl reference): the workload is the same, what each arm executes of it per step is
+    said in `cpu_baseline.sample` on the reference side."""
+    return {"workload": "c3: synthetic n=1024, 16 objects x 64, nX=10, nU=1, 512 chains per GPU; step = 1 MH sweep "
+                        "(58 single-site updates) of every chain; continuous T, default InvGamma(4,4) priors",
+            "chains_per_gpu": WORKLOAD["chains_per_gpu"], "sites_per_sweep": S,
+            "l2": "working set (296 resident factor scratch slots x 4.25 MiB = 1.26 GB) exceeds the 126 MB L2; no explicit flush",
+            "seed": 1234}
+
+
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
-def cpu_sample(mode="faithful"):
+def cpu_sample(mode="faithful", chain=0):
     """Bounded sample of the SAME workload on the host cores: single-site MH updates of one sweep of one chain executed by the
     NumPy/SciPy oracle port. mode "faithful" = the reference's cost model (every update re-scores the whole model: nX+5 kernel
     builds and nU+nX+2 Choleskys, the U-prior one included — SURVEY.md §3.2); "incremental" = one build + one Cholesky per update
@@ -129,7 +141,7 @@ def cpu_sample(mode="faithful"):
     w = WORKLOAD
     counts, X, T, Y = od.synthetic(w["n"], w["n_obj"], w["nX"])
     md = od.model_data_from_arrays(counts, X, T, Y, nU=w["nU"])
-    st = oi.generate_initial_state(md, 1234, 0)
+    st = oi.generate_initial_state(md, 1234, chain)
     sc = oi.Scorer(md, st, mode)
     sites = md.spec.mh_sites()
 
@@ -137,9 +149,63 @@ def cpu_sample(mode="faithful"):
         t = time.perf_counter()
         for s in range(first, first + count):
             name, a, b = sites[s % len(sites)]
-            oi.mh_site(md, st, sc, s % len(sites), name, a, b, 1234, 0, s // len(sites))
+            oi.mh_site(md, st, sc, s % len(sites), name, a, b, 1234, chain, s // len(sites))
         return time.perf_counter() - t
     return run, len(sites)
+
+
+def _chain_worker(chain, mode, sites_per_step, warmup, steps, gate, q):
+    """One host process = one chain of the workload with ONE BLAS thread (the reference is single-threaded Julia per chain): `warmup`
+    untimed and `steps` timed groups of `sites_per_step` single-site updates, all workers released together."""
+    try:
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(limits=1):
+            run, S = cpu_sample(mode, chain)
+            pos = 0
+            for _ in range(warmup):
+                run(pos, sites_per_step); pos += sites_per_step
+            gate.wait()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                run(pos, sites_per_step); pos += sites_per_step
+            q.put((chain, time.perf_counter() - t0, S))
+    except Exception as e:      # a dead worker must not leave the others at the gate
+        try:
+            gate.abort()
+        except Exception:
+            pass
+        q.put((chain, None, repr(e)))
+
+
+def cpu_many_chains(mode, sites_per_step, warmup, steps, workers=None):
+    """The many-chain workload on all host cores: `workers` (default: every core) independent chains of it, one process and one BLAS
+    thread each. Returns (aggregate sweeps/s, wall seconds of the slowest worker, sites per sweep, workers)."""
+    import multiprocessing as mp
+    P = workers or os.cpu_count() or 1
+    ctxm = mp.get_context("spawn")
+    gate, q = ctxm.Barrier(P), ctxm.Queue()
+    saved = {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
+    for k in saved:
+        os.environ[k] = "1"       # inherited by the spawned interpreters before they load a BLAS
+    try:
+        procs = [ctxm.Process(target=_chain_worker, args=(c, mode, sites_per_step, warmup, steps, gate, q), daemon=True) for c in range(P)]
+        for pr in procs:
+            pr.start()
+        res = [q.get() for _ in range(P)]
+        for pr in procs:
+            pr.join(30)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    bad = [r for r in res if r[1] is None]
+    if bad:
+        raise RuntimeError(f"CPU baseline worker failed: {bad[0][2]}")
+    T = max(r[1] for r in res)
+    S = res[0][2]
+    return P * steps * sites_per_step / S / T, T, S, P
 
 
 def cpu_variants(budget_s=22.0):
@@ -183,28 +249,21 @@ def cpu_c1():
 
 
 def run_reference(args):
+    """--impl reference: the reference's algorithm for this path (oracle port with the reference's cost model; Julia / Gen.jl cannot run
+    here) on the box's host cores, on the same workload: as many of its independent chains as there are cores, one process and one
+    BLAS thread per chain - the reference itself is single-threaded per chain -, a bounded number of single-site updates per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    run, S = cpu_sample("faithful")
-    sites_per_step = 6
-    pos = 0
-    for _ in range(args.warmup):
-        run(pos, sites_per_step); pos += sites_per_step
-    t = 0.0
-    for _ in range(args.steps):
-        t += run(pos, sites_per_step); pos += sites_per_step
-    sweeps = args.steps * sites_per_step / S
-    value = sweeps / t
-    cores = os.cpu_count()
-    sample = (f"{sites_per_step} of the {S} single-site MH updates of one sweep of ONE chain per step at the c3 shape "
-              f"(n=1024, nX=10, nU=1), reference cost model (full model re-score per update: 15 kernel builds + 13 Choleskys), "
-              f"NumPy/SciPy oracle port, BLAS threads = all {cores} host cores; scaled to sweeps/s")
+    sites_per_step = 3
+    value, T, S, P = cpu_many_chains("faithful", sites_per_step, args.warmup, args.steps)
+    sample = (f"{P} of the 512 chains (one per host core, one BLAS thread each), {sites_per_step} of the {S} single-site MH updates of a "
+              f"sweep per step at the c3 shape (n=1024, nX=10, nU=1), reference cost model (full model re-score per update: 15 kernel "
+              f"builds + 13 Choleskys), NumPy/SciPy oracle port; sweeps/s summed over the {P} chains")
     line = {"impl": "reference", "metric": "mh_sweeps_per_sec", "value": value, "unit": "sweeps/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "c3: n=1024, 16 objects, nX=10, nU=1; one chain on the host (the reference is single-chain, single-process)"},
-            "cpu_baseline": {"value": value, "unit": "sweeps/s", "cores": cores, "kind": "port", "sample": sample},
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * T / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": bench_config(S),
+            "cpu_baseline": {"value": value, "unit": "sweeps/s", "cores": P, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -419,11 +478,7 @@ def run_ours(args):
         line = {"metric": "mh_sweeps_per_sec", "value": value, "unit": "sweeps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "c3: synthetic n=1024, 16 objects x 64, nX=10, nU=1, 512 chains per GPU; step = 1 MH sweep "
-                                       "(58 single-site updates) of every chain; continuous T, default InvGamma(4,4) priors",
-                           "chains_per_gpu": C, "sites_per_sweep": S,
-                           "l2": "working set (296 resident factor scratch slots x 4.25 MiB = 1.26 GB) exceeds the 126 MB L2; no explicit flush",
-                           "seed": 1234},
+                "config": bench_config(S),
                 "clocks": clk, "gpu_launches": int(launches), "e2e": e2e,
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                              "traffic": ncu_traffic(), "kernel": "mh_lanes_kernel (fused RBF build + blocked Cholesky + solve, DMMA)",
@@ -437,11 +492,14 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             v = cpu_variants()
             v["c1_seconds"] = cpu_c1()
-            fa = v["faithful_all_cores"]
-            line["cpu_baseline"] = {"value": fa["value"], "unit": "sweeps/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"{fa['sites_timed']} of 58 single-site MH updates of one sweep of one chain at the c3 shape, "
-                                              "reference cost model (full model re-score per update, U-prior Cholesky executed), NumPy/SciPy "
-                                              f"oracle port with BLAS threads = all {os.cpu_count()} host cores; {fa['seconds']:.1f} s of CPU work",
+            mv, mT, mS, mP = cpu_many_chains("faithful", 6, 1, 3)
+            v["faithful_many_chains"] = {"value": mv, "unit": "sweeps/s (summed over the chains)", "chains": mP, "blas_threads": 1,
+                                         "sites_timed": 18, "seconds": mT}
+            line["cpu_baseline"] = {"value": mv, "unit": "sweeps/s", "cores": mP, "kind": "port",
+                                    "sample": f"{mP} of the 512 chains, one process with one BLAS thread per host core, 18 of {mS} single-site MH "
+                                              "updates of one sweep each at the c3 shape, reference cost model (full model re-score per update, "
+                                              "U-prior Cholesky executed), NumPy/SciPy oracle port; sweeps/s summed over the chains; "
+                                              f"{mT:.1f} s wall ({mP * mT:.0f} s of CPU work)",
                                     "variants": v}
         emit(line)
     ctx.close()
