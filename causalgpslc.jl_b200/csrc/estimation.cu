@@ -234,7 +234,7 @@ ite_kernel(EstArgs a, double* scratch, size_t slot_scratch, double* zbuf, size_t
     const unsigned int team = TEAM ? cluster_id_x() : blockIdx.x, nteams = TEAM ? cluster_count_x() : gridDim.x;
     double* my_scratch = scratch + (size_t)team * slot_scratch;
     double* my_z = zbuf + (size_t)blockIdx.x * slot_z;
-    double* xi = xibuf + (size_t)blockIdx.x * 4 * a.n;
+    double* xi = xibuf + (size_t)blockIdx.x * 8 * npad;      // [8 draws][npad columns]
     const unsigned int nbase = (unsigned)a.n_chains * a.R;
     const unsigned int total = PRE ? (unsigned)a.n_doT * a.base_n : (unsigned)a.n_doT * nbase;
     // PRE: the lower-left and lower-right blocks only (block rows >= NCB1) live in this task's scratch
@@ -271,36 +271,47 @@ ite_kernel(EstArgs a, double* scratch, size_t slot_scratch, double* zbuf, size_t
         const double* wres = my_z + (size_t)MAXRHS * (2 * npad) + npad;
         if (a.mean_out && trank == 0)
             for (int i = threadIdx.x; i < a.n; i += blockDim.x) a.mean_out[(size_t)t * a.n + i] = -wres[i];
-        // draws: MeanITE + L22 xi   (src/estimation.jl:95-109; one factor serves all spp draws); rows are split across the team
+        // draws: MeanITE + L22 xi   (src/estimation.jl:95-109; one factor serves all spp draws), eight draws at a time as a tensor-core
+        // product: the scratch's atom layout IS the DMMA A-fragment layout (one coalesced 256-byte load per 8 x 4 piece of L22), the B
+        // fragment is xi[4 columns][8 draws]. 8-row groups are dealt to the warps (and, in team mode, to the CTAs of the team); the
+        // blocks above the diagonal are never touched and the diagonal blocks hold zeros above the diagonal. (The first version walked
+        // L22 one row per thread through elem_off: 4.6 ms per task at n = 1024 and 10 draws, latency-bound - 15 % of the task.)
         if (a.ite_out && a.spp > 0) {
             const unsigned gchain = (unsigned)(a.chain0 + c);
-            for (int s0 = 0; s0 < a.spp; s0 += 4) {
-                const int ns = min(4, a.spp - s0);
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            const int g = lane >> 2, q = lane & 3;
+            const int ngroups = (a.n + 7) >> 3;
+            for (int s0 = 0; s0 < a.spp; s0 += 8) {
+                const int ns = min(8, a.spp - s0);
                 __syncthreads();
-                for (int e = threadIdx.x; e < ns * a.n; e += blockDim.x) {
-                    const int s = e / a.n, col = e - s * a.n;
-                    Stream st(a.seed, gchain, (uint32_t)(r * a.spp + s0 + s), stream_b(TAG_ITE, (uint32_t)(a.dot0 + d)));
-                    xi[(size_t)s * a.n + col] = st.normal_at(col);
+                for (int e = threadIdx.x; e < 8 * npad; e += blockDim.x) {
+                    const int s = e / npad, col = e - s * npad;
+                    double v = 0.0;                     // unused draws and the padding columns multiply zeros / identity padding
+                    if (s < ns && col < a.n) {
+                        Stream st(a.seed, gchain, (uint32_t)(r * a.spp + s0 + s), stream_b(TAG_ITE, (uint32_t)(a.dot0 + d)));
+                        v = st.normal_at(col);
+                    }
+                    xi[(size_t)s * npad + col] = v;
                 }
                 __syncthreads();
-                for (int i = trank * blockDim.x + threadIdx.x; i < a.n; i += tsize * blockDim.x) {
-                    double accv[4] = {0.0, 0.0, 0.0, 0.0};
-                    const int I = NCB1 + (i >> 6), ri = i & 63;
-                    for (int jb = 0; jb <= (i >> 6); jb++) {
-                        const double* blk = my_scratch + (block_off(I, NCB1 + jb, NCB) - hi_off);
-                        const int jmax = (jb == (i >> 6)) ? ri : 63;
-                        for (int jj = 0; jj <= jmax; jj++) {
-                            const double l = blk[elem_off(ri, jj)];
-                            const int col = jb * 64 + jj;
-                            if (col < a.n) {
-#pragma unroll
-                                for (int s = 0; s < 4; s++)
-                                    if (s < ns) accv[s] = fma(l, xi[(size_t)s * a.n + col], accv[s]);
-                            }
-                        }
+                for (int rg = trank * FWARPS + warp; rg < ngroups; rg += tsize * FWARPS) {
+                    const int ib = rg >> 3, r8 = rg & 7;
+                    double acc[2] = {0.0, 0.0};
+                    const double* xq = xi + (size_t)g * npad + q;          // B fragment: B[k = q][n = g] = xi[draw g][column c0 + q]
+                    for (int jb = 0; jb <= ib; jb++) {
+                        const double* blk = my_scratch + (block_off(NCB1 + ib, NCB1 + jb, NCB) - hi_off) + r8 * (K4S * 32) + lane;
+                        const double* xb = xq + jb * NB;
+#pragma unroll 4
+                        for (int kk = 0; kk < NB / 4; kk++)                // slab kk / 4, k4 = kk % 4: atoms of one row group are 256 B apart
+                            dmma(acc, blk[(kk >> 2) * SLAB_D + (kk & 3) * 32], xb[kk * 4]);
                     }
-                    for (int s = 0; s < ns; s++)
-                        a.ite_out[(((size_t)d * a.n_chains + c) * a.R * a.spp + (size_t)r * a.spp + s0 + s) * a.n + i] = -wres[i] + accv[s];
+                    const int row = rg * 8 + g;
+                    if (row < a.n) {
+                        const double m = -wres[row];
+                        double* o = a.ite_out + (((size_t)d * a.n_chains + c) * a.R * a.spp + (size_t)r * a.spp + s0) * a.n + row;
+                        if (2 * q < ns) o[(size_t)(2 * q) * a.n] = m + acc[0];
+                        if (2 * q + 1 < ns) o[(size_t)(2 * q + 1) * a.n] = m + acc[1];
+                    }
                 }
             }
         }
@@ -535,7 +546,7 @@ static int launch_ite_shared(Ctx* ctx, const EstArgs& a0) {
             GP_TRY(ensure_workspace(ctx, NCB, NCB, total, &grid, team, NCB1));
             if (team > 1) GP_TRY(clip_to_resident_clusters(ctx, ite_kernel<1, true>, team, grid, &grid));
             GP_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, sizeof(unsigned int), ctx->stream));
-            const size_t need_xi = (size_t)grid * team * 4 * a.n * sizeof(double);
+            const size_t need_xi = (size_t)grid * team * 8 * npad * sizeof(double);
             if (need_xi > xi_cap) { GP_CUDA(ctx, ctx->arena_alloc(reinterpret_cast<void**>(&xi), need_xi)); xi_cap = need_xi; }
             GP_TRY(launch_ite_kernel<true>(ctx, a, team, grid, xi));
         }
@@ -560,7 +571,7 @@ int launch_ite(Ctx* ctx, const EstArgs& a) {
     if (team > 1) GP_TRY(clip_to_resident_clusters(ctx, ite_kernel<1, false>, team, grid, &grid));
     GP_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, sizeof(unsigned int), ctx->stream));
     double* xi = nullptr;
-    GP_CUDA(ctx, ctx->arena_alloc(reinterpret_cast<void**>(&xi), (size_t)grid * team * 4 * a.n * sizeof(double)));
+    GP_CUDA(ctx, ctx->arena_alloc(reinterpret_cast<void**>(&xi), (size_t)grid * team * 8 * (NCB / 2) * NB * sizeof(double)));
     int rc = launch_ite_kernel<false>(ctx, a, team, grid, xi);
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
     if (rc) return rc;
