@@ -45,7 +45,10 @@ constexpr int BLOCK_D = NB * NB;       // doubles per block (32 KB)
 #define GPSLC_CTAS 2           // resident factor CTAs per SM the kernels are built for (3: experiment with a two-stage operand ring)
 #endif
 constexpr int CTAS_PER_SM = GPSLC_CTAS;
-constexpr int STAGES = (GPSLC_CTAS >= 3) ? 2 : 3;
+#ifndef GPSLC_STAGES
+#define GPSLC_STAGES ((GPSLC_CTAS >= 3) ? 2 : 3)
+#endif
+constexpr int STAGES = GPSLC_STAGES;
 constexpr int FWARPS = 8;
 constexpr int FTHREADS = FWARPS * 32;
 constexpr int STAGE_D = 3 * SLAB_D;    // A0 | A1 | B
