@@ -844,6 +844,59 @@ def test_subgroup_effect_curve_matches_the_documented_workflow(ctx):
         ge_.subset_mean(lay, np.zeros(len(idx), bool), ctx=ctx)                 # empty subgroup is an argument error
 
 
+def test_device_resident_buffers_through_the_c_abi(ctx):
+    """GPSLC_DEVICE (include/gpslc.h): the estimation entry points take and return DEVICE pointers, so a counterfactual sweep is
+    summarised where gpslc_ite left it in HBM. Device-mode results must equal host-mode results bit for bit: gpslc_ite (mean, draws,
+    info) -> gpslc_summarize and gpslc_subset_mean on the device draws; gpslc_ite_subset_summary with device outputs."""
+    import ctypes
+    import torch
+    from gpslc_b200 import DEVICE
+    from gpslc_b200.estimation import _bind_est, _data_struct
+    from gpslc_b200.inference import _bind
+    _bind(ctx.lib); _bind_est(ctx.lib)
+    n, nX = 90, 2
+    counts, X, T, Y = od.synthetic(n, 3, nX, seed=21)
+    h = g.getHyperParameters(); h.nOuter, h.nBurnIn = 5, 2
+    gobj = g.gpslc(counts, X, T, Y, hyperparams=h, seed=4, ctx=ctx)
+    packed = np.ascontiguousarray(gobj.posteriorPacked[:, :1])
+    n_outer, C, stride = packed.shape
+    ret = np.arange(1, 5, dtype=np.int32); R, spp = len(ret), 3
+    doT = np.array([0.2, -0.4]); D = len(doT)
+    host = ge.ite(packed, X, T, Y, 1, doT, ret, 1e-10, spp, seed=9, ctx=ctx)
+    dev = torch.device("cuda", 0)
+    dt = lambda a, dtype=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device=dev)
+    Xd, Td, Yd, Sd = dt(np.asfortranarray(X).T.copy()), dt(T), dt(Y), dt(packed)     # X column-major n x nX
+    d, _keep = _data_struct(X, T, Y, 1)
+    d.X, d.T, d.Y = Xd.data_ptr(), Td.data_ptr(), Yd.data_ptr()
+    mean_d = torch.empty((D, C, R, n), dtype=torch.float64, device=dev)
+    draws_d = torch.empty((D, C, R * spp, n), dtype=torch.float64, device=dev)
+    info_d = torch.empty((D, C, R), dtype=torch.int32, device=dev)
+    ctx.check(ctx.lib.gpslc_ite(ctx.h, DEVICE, ctypes.byref(d), Sd.data_ptr(), n_outer, C, stride, ret.ctypes.data, R, doT.ctypes.data, D,
+                                1e-10, spp, 9, 0, mean_d.data_ptr(), None, draws_d.data_ptr(), info_d.data_ptr()))
+    torch.cuda.synchronize()
+    assert np.array_equal(mean_d.cpu().numpy(), host["mean"]) and np.array_equal(draws_d.cpu().numpy(), host["samples"])
+    assert int(info_d.abs().max()) == 0
+    # summarise / subgroup-average the device draws in place
+    summ_d = torch.empty((D * C, n, 3), dtype=torch.float64, device=dev)
+    ctx.check(ctx.lib.gpslc_summarize(ctx.h, DEVICE, draws_d.data_ptr(), D * C, R * spp, n, 0.9, summ_d.data_ptr()))
+    want = ge.summarize(host["samples"].reshape(D * C, R * spp, n), 0.9, ctx=ctx)
+    assert np.array_equal(summ_d.cpu().numpy(), want)
+    mask = np.zeros(n, dtype=np.uint8); mask[5:40:3] = 1
+    sub_d = torch.empty((D * C, R * spp), dtype=torch.float64, device=dev)
+    ctx.check(ctx.lib.gpslc_subset_mean(ctx.h, DEVICE, draws_d.data_ptr(), D * C, R * spp, n, mask.ctypes.data, sub_d.data_ptr()))
+    assert np.array_equal(sub_d.cpu().numpy(), ge.subset_mean(host["samples"].reshape(D * C, R * spp, n), mask, ctx=ctx))
+    assert np.allclose(sub_d.cpu().numpy(), host["samples"].reshape(D * C, R * spp, n)[:, :, mask.astype(bool)].mean(axis=2), rtol=1e-13, atol=1e-14)
+    # fused subgroup summary with device outputs == host-mode call
+    hs, hsub, hinfo = ge.ite_subset_summary(packed, X, T, Y, 1, doT, ret, 1e-10, spp, mask, seed=9, ctx=ctx)
+    fs_d = torch.empty((C, D, 3), dtype=torch.float64, device=dev); fsub_d = torch.empty((C, R * spp, D), dtype=torch.float64, device=dev)
+    ctx.check(ctx.lib.gpslc_ite_subset_summary(ctx.h, DEVICE, ctypes.byref(d), Sd.data_ptr(), n_outer, C, stride, ret.ctypes.data, R,
+                                               doT.ctypes.data, D, 0, 1e-10, spp, 9, 0, mask.ctypes.data, 0.9, fsub_d.data_ptr(),
+                                               fs_d.data_ptr(), info_d.data_ptr()))
+    torch.cuda.synchronize()
+    assert np.array_equal(fs_d.cpu().numpy(), hs) and np.array_equal(fsub_d.cpu().numpy(), hsub)
+    assert np.allclose(hsub[0].T, host["samples"][:, 0][:, :, mask.astype(bool)].mean(axis=2), rtol=1e-13, atol=1e-14)
+
+
 def test_binary_treatment_end_to_end_ihdp(ctx):
     """IHDP_sampled.csv (n=272, 6 covariates, 200 objects, Bool T): gpslc -> sampleITE(true/false) -> summarizeEstimates through the
     public API runs the binary-T sampler (logitT slices); ONE default chain must pass the reference's own gate against the golden
