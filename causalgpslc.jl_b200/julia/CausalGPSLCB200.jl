@@ -88,13 +88,16 @@ function to_choicemap(rec::AbstractVector{Float64}, n, nU, nX, X, T, Y, binary)
     cm = Gen.choicemap()
     names = (:uNoise, :tNoise, :yNoise, :tyLS, :tScale, :yScale)
     for (k, s) in enumerate(names); isnan(rec[k]) || (cm[s] = rec[k]); end
+    np = 6 + 4nX + 2nU + nU * nX
+    # no-U models never observe X (SURVEY.md App. B3): the record then carries the model's own X after U / logitT (include/gpslc.h, stride)
+    xoff = np + nU * n + (binary ? n : 0)
+    has_xmodel = nU == 0 && nX > 0 && length(rec) >= xoff + n * nX
     for k in 1:nX
         isnan(rec[6+k]) || (cm[:xNoise=>k=>:Noise] = rec[6+k])
         isnan(rec[6+nX+k]) || (cm[:xScale=>k=>:Scale] = rec[6+nX+k])
         cm[:xtLS=>k=>:LS] = rec[6+2nX+k]; cm[:xyLS=>k=>:LS] = rec[6+3nX+k]
-        cm[:X=>k=>:X] = X[:, k]
+        cm[:X=>k=>:X] = has_xmodel ? rec[xoff+(k-1)*n+1:xoff+k*n] : X[:, k]
     end
-    np = 6 + 4nX + 2nU + nU * nX
     for i in 1:nU
         cm[:utLS=>i=>:LS] = rec[6+4nX+i]; cm[:uyLS=>i=>:LS] = rec[6+4nX+nU+i]
         for j in 1:nX; cm[:uxLS=>i=>j=>:LS] = rec[6+4nX+2nU+(i-1)*nX+j]; end
@@ -239,10 +242,10 @@ exactly the unsharded result. Returns (ite[d_local, n, R*spp], the full doT rang
 function predictCounterfactualEffectsShard(g, nSamplesPerMixture::Int, world_size::Int, rank::Int; fidelity::Int=100,
                                            minDoT=min(g.T...), maxDoT=max(g.T...), seed=UInt64(0))   # all ranks must pass the SAME seed
     doTrange = minDoT:(abs(maxDoT - minDoT) / fidelity):maxDoT
-    all = collect(Float64, doTrange); D = length(all)
+    alldts = collect(Float64, doTrange); D = length(alldts)
     base, rem = divrem(D, world_size)
     cnt = base + (rank < rem ? 1 : 0); off = rank * base + min(rank, rem)
-    dts = all[off+1:off+cnt]
+    dts = alldts[off+1:off+cnt]
     packed = pack(g); ret = retained(g.hyperparams); R = length(ret); n = length(g.Y)
     Tf = Float64.(g.T); Xf = g.X === nothing ? Float64[] : Matrix{Float64}(g.X); Yf = Float64.(g.Y)
     out = Array{Float64}(undef, n, R * nSamplesPerMixture, cnt)
@@ -267,10 +270,10 @@ device through gpslc_ite_summary: the ITE draws of this rank's block of doT valu
 function predictCounterfactualSummaryShard(g, nSamplesPerMixture::Int, world_size::Int, rank::Int; fidelity::Int=100,
                                            minDoT=min(g.T...), maxDoT=max(g.T...), seed=UInt64(0), credible_interval::Float64=0.90)
     doTrange = minDoT:(abs(maxDoT - minDoT) / fidelity):maxDoT
-    all = collect(Float64, doTrange); D = length(all)
+    alldts = collect(Float64, doTrange); D = length(alldts)
     base, rem = divrem(D, world_size)
     cnt = base + (rank < rem ? 1 : 0); off = rank * base + min(rank, rem)
-    dts = all[off+1:off+cnt]
+    dts = alldts[off+1:off+cnt]
     packed = pack(g); ret = retained(g.hyperparams); R = length(ret); n = length(g.Y)
     Tf = Float64.(g.T); Xf = g.X === nothing ? Float64[] : Matrix{Float64}(g.X); Yf = Float64.(g.Y)
     out = Array{Float64}(undef, 3, n, cnt)                           # C layout [d_local][1][n][3]
@@ -296,10 +299,10 @@ block of doT values: `summary[3, d_local]` = (Mean, LowerBound, UpperBound) per 
 function subgroupEffectCurveShard(g, idx::AbstractVector{Bool}, nSamplesPerMixture::Int, world_size::Int, rank::Int; fidelity::Int=100,
                                   minDoT=min(g.T...), maxDoT=max(g.T...), seed=UInt64(0), credible_interval::Float64=0.90)
     doTrange = minDoT:(abs(maxDoT - minDoT) / fidelity):maxDoT
-    all = collect(Float64, doTrange); D = length(all)
+    alldts = collect(Float64, doTrange); D = length(alldts)
     base, rem = divrem(D, world_size)
     cnt = base + (rank < rem ? 1 : 0); off = rank * base + min(rank, rem)
-    dts = all[off+1:off+cnt]
+    dts = alldts[off+1:off+cnt]
     packed = pack(g); ret = retained(g.hyperparams); R = length(ret); n = length(g.Y)
     length(idx) == n || throw(ArgumentError("idx must have one entry per individual"))
     mask = UInt8.(idx)
