@@ -265,3 +265,29 @@ def test_gpslc_file_round_trip(tmp_path):
     with pytest.raises(ValueError):
         (tmp_path / "junk.gpslc").write_bytes(b"not a gpslc file at all")
         g.loadGPSLCObject(str(tmp_path / "junk"))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's algorithm on the host cores, oracle port): ONE JSON line on stdout with the GPU
+    arm's metric / unit / config, `impl`, a `cpu_baseline` describing the run and an `e2e` equal to the value with zero copy bytes."""
+    import json, subprocess, sys
+    root = os.path.join(os.path.dirname(__file__), "..")
+    sys.path.insert(0, root)
+    import bench
+    env = dict(os.environ); env.pop("RANK", None)
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "mh_sweeps_per_sec" and d["unit"] == "sweeps/s" and d["higher_is_better"] is True
+    assert d["config"] == bench.bench_config(58) and d["dtype"] == "f64" and d["vs_baseline"] is None
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == os.cpu_count() and cb["value"] == d["value"] > 0 and "chains" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # ranks other than 0 of a torchrun launch do no work and print nothing
+    env["RANK"] = "1"
+    r1 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                        capture_output=True, text=True, timeout=120, env=env)
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
