@@ -100,7 +100,7 @@ struct IteGen {
         const int n = s->n, np = s->npad, D = s->D;
         const bool r2 = r0 >= np, c2 = c0 >= np;
         const int i0 = r2 ? r0 - np : r0, i1 = r2 ? r1 - np : r1, j0 = c2 ? c0 - np : c0;
-        if (D + 2 <= CF_DIMS && i0 < n && i1 < n && j0 + 8 * (NI - 1) + 1 < n) {
+        if (D + 2 <= CF_DIMS && i0 < n && (ONE_ROW || i1 < n) && j0 + 8 * (NI - 1) + 1 < n) {
             double a[2][NI][2];
 #pragma unroll
             for (int ni = 0; ni < NI; ni++) { a[0][ni][0] = 0.0; a[0][ni][1] = 0.0; a[1][ni][0] = 0.0; a[1][ni][1] = 0.0; }

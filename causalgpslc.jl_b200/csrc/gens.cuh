@@ -117,7 +117,8 @@ struct RbfGen {
         const int D = s->D;
         // fast path: all entries inside the matrix and the panel's column features staged in shared memory (D <= CF_DIMS); otherwise
         // (ragged edge, or more dimensions than the staging area holds) the element-wise path below, which gives the same values
-        if (r1 < n && r0 < n && c0 + 8 * (NI - 1) + 1 < n && GPSLC_STAGE_COLS && D <= CF_DIMS) {
+        // (a ONE_ROW caller's r1 is a dummy: testing it sent the warp that owns the last 8 rows of the matrix down the element-wise path)
+        if ((ONE_ROW || r1 < n) && r0 < n && c0 + 8 * (NI - 1) + 1 < n && GPSLC_STAGE_COLS && D <= CF_DIMS) {
             double a[2][NI][2];
 #pragma unroll
             for (int ni = 0; ni < NI; ni++) { a[0][ni][0] = 0.0; a[0][ni][1] = 0.0; a[1][ni][0] = 0.0; a[1][ni][1] = 0.0; }
